@@ -1,0 +1,149 @@
+/*
+ * rvh.h -- C ABI of the B200-native guide-strand physics step (librvh.so).
+ *
+ * Drop-in boundary for ONE path of clach/Realtime-Vulkan-Hair: the per-frame
+ * Follow-the-Leader / PBD compute pass (src/shaders/compute.comp).  The reference has no
+ * FFI seam; its physics is reached only through Vulkan objects.  Each entry point below
+ * names the reference call site it replaces (file:line relative to the reference tree).
+ * The C++ host mirror that keeps the reference's Hair / Scene / Renderer signatures on
+ * top of this ABI lives in realtime-vulkan-hair_b200/host/; the binding a maintainer
+ * would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 (RVH_OK) or a negative rvh_status;
+ *     nothing throws across the boundary (reference convention is
+ *     `throw std::runtime_error`, e.g. Renderer.cpp:2317-2319 -- the C++ mirror converts).
+ *   - the caller owns every host pointer; data is copied during the call.
+ *   - one context = one CUDA device + one stream; calls on a context are not re-entrant
+ *     (the reference is single-threaded with one frame in flight, main.cpp:257-285).
+ *   - there is NO CPU fallback: without a CUDA device rvh_create fails.
+ *
+ * Buffer layouts (bit-for-bit the reference's):
+ *   Strand[S]           float [S][3][N][4]: curvePoints, curveVels, correctionVecs
+ *                       (Strand.h:11-15; compute.comp:44-48), N generalised from 10
+ *   Collider[n]         3 column-major mat4: transform, inv, invTrans = 192 B
+ *                       (Scene.h:23-26; compute.comp:25-33); index 0 is the sphere
+ *   StrandDrawIndirect  4 x uint32 (Strand.h:53-58)
+ *   grid download       int64 [G^3][4] = (vel.x, vel.y, vel.z, density), fixed point
+ *                       x grid_scale; with RVH_GRID_INT32_WRAP: int32 [G^3][4], the
+ *                       reference's GridCell (Scene.h:42-49; compute.comp:35-42)
+ */
+#ifndef RVH_H
+#define RVH_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rvh_ctx rvh_ctx;
+
+typedef enum {
+    RVH_OK = 0,
+    RVH_ERR_INVALID = -1,   /* bad argument / size mismatch                 */
+    RVH_ERR_CUDA = -2,      /* CUDA runtime error (message in last_error)   */
+    RVH_ERR_NCCL = -3,      /* NCCL not loadable or a collective failed     */
+    RVH_ERR_STATE = -4      /* call order (e.g. step before upload)         */
+} rvh_status;
+
+enum {
+    RVH_GRID_ON         = 1,   /* hair-hair friction through the voxel grid, compute.comp:211-298 */
+    RVH_WIND_A          = 2,   /* compute.comp:151 (commented out in the reference)              */
+    RVH_WIND_B          = 4,   /* compute.comp:152 (commented out in the reference)              */
+    RVH_GRID_INT32_WRAP = 8,   /* read the grid back through its low 32 bits = reference int32   */
+    RVH_KEEP_CORRECTION = 16,  /* also store correctionVecs (dead across steps; download only)   */
+    RVH_KEEP_ORDER      = 32   /* no internal Morton reordering of strands                       */
+};
+
+typedef struct {              /* every field defaults to the reference constant     */
+    int   device;             /* CUDA ordinal                                       */
+    int   num_strands;        /* S (strands owned by this context)                  */
+    int   num_points;         /* N >= 2, root included      compute.comp:5          */
+    float rest_length;        /* "radius" 2.5f/(N-1)        compute.comp:139-140    */
+    float gravity_y;          /* -9.8f                      compute.comp:150        */
+    float damping;            /* 0.998f                     compute.comp:7          */
+    float vmax;               /* 10.f                       compute.comp:198        */
+    float penalty_k;          /* 1900.f                     compute.comp:163,173    */
+    float sphere_radius;      /* 1.f                        compute.comp:161        */
+    int   grid_dim;           /* 64                         compute.comp:9          */
+    float grid_extent;        /* 7.f                        compute.comp:10         */
+    float grid_origin[3];     /* -3,-2,-5                   compute.comp:206        */
+    float grid_scale;         /* 1e6f                       compute.comp:11         */
+    float friction;           /* 0.08f                      compute.comp:296        */
+    int   flags;              /* RVH_* bits; default RVH_GRID_ON                    */
+    int   strands_per_thread; /* 0 = auto; 1, 2 or 4 (tuning, results identical)    */
+} rvh_config;
+
+/* Fill cfg with the reference constants for S strands of N points. */
+void rvh_default_config(rvh_config* cfg, int num_strands, int num_points);
+
+/* Replaces Renderer::Create{Time,Colliders,Grid,Compute}DescriptorSetLayout
+ * (Renderer.cpp:402-497), the matching descriptor sets (836-997), CreateComputePipeline
+ * (1748-1788) and RecordComputeCommandBuffer (2022-2077); allocates the grid that
+ * Scene::Scene uploads (Scene.cpp:16-20). */
+int rvh_create(rvh_ctx** out, const rvh_config* cfg);
+
+/* Multi-GPU: this context owns one contiguous shard of the strands; the voxel grid is
+ * all-reduced with NCCL once per step.  nccl_unique_id is the 128-byte ncclUniqueId
+ * from rvh_nccl_unique_id() on rank 0, distributed by the launcher. */
+int rvh_nccl_unique_id(void* out128);
+int rvh_create_sharded(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, const void* nccl_unique_id);
+
+/* Collider UBO write: Scene::Scene memcpy (Scene.cpp:10-13) and Scene::translateSphere
+ * (Scene.cpp:133).  colliders = n x 192 bytes, n <= 8. */
+int rvh_set_colliders(rvh_ctx* ctx, const void* colliders, int n);
+
+/* Hair::Hair's strands upload (Strand.cpp:188).  bytes must be S*48*N. */
+int rvh_upload_strands_aos(rvh_ctx* ctx, const void* strands, size_t bytes);
+
+/* Vulkan interop: map the exported strands VkBuffer (VK_KHR_external_memory_fd) and
+ * keep it updated after every step in the reference's AoS vertex-buffer layout
+ * (Renderer.cpp:2153-2161 binds it).  Needs a Vulkan device on the caller's side. */
+int rvh_import_strands_fd(rvh_ctx* ctx, int fd, size_t bytes);
+
+/* vkQueueSubmit(Compute, computeCommandBuffer) in Renderer::Frame (Renderer.cpp:2311-2319):
+ * grid clear + one pass of compute.comp.  dt / total_time are Scene::UpdateTime's values
+ * (Scene.cpp:78-87).  Asynchronous on the context's stream. */
+int rvh_step(rvh_ctx* ctx, float dt, float total_time);
+
+/* n back-to-back steps, total_time advancing by dt; if ms_out != NULL the whole batch is
+ * timed with CUDA events on the context's stream and the call synchronises. */
+int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out);
+
+/* Host round trip in one call: upload Strand[S], one step, download Strand[S]. */
+int rvh_step_host(rvh_ctx* ctx, void* strands_inout, size_t bytes, float dt, float total_time);
+
+/* Read-backs (synchronise).  The reference never reads these back; tests do. */
+int rvh_download_strands_aos(rvh_ctx* ctx, void* strands, size_t bytes);
+int rvh_download_grid(rvh_ctx* ctx, void* cells, size_t bytes);
+int rvh_draw_indirect(rvh_ctx* ctx, uint32_t out[4]);   /* {S,1,0,0}, compute.comp:126-130,302 */
+
+/* Debug/test hooks: run the step split at the shader's barriers.  phase bits:
+ * 1 = integrate+FTL (+corrected velocity, + splat when the grid is on), 2 = gather. */
+int rvh_step_phases(rvh_ctx* ctx, float dt, float total_time, int phases);
+
+/* Per-kernel CUDA-event timing (for the roofline figure).  When enabled every step
+ * brackets its kernels with events; rvh_profile_read returns accumulated milliseconds
+ * and launch counts since the last call: [0] ftl_step, [1] grid_gather, [2] grid
+ * all-reduce, [3] grid clear. */
+int rvh_profile_enable(rvh_ctx* ctx, int on);
+int rvh_profile_read(rvh_ctx* ctx, float ms[4], int launches[4]);
+
+int rvh_sync(rvh_ctx* ctx);
+float rvh_last_step_ms(rvh_ctx* ctx);
+long long rvh_kernel_launches(rvh_ctx* ctx);            /* kernels launched so far */
+const char* rvh_last_error(rvh_ctx* ctx);               /* ctx may be NULL: create errors */
+void rvh_destroy(rvh_ctx* ctx);
+
+/* Host-side helpers mirroring reference host code (no GPU needed). */
+void  rvh_collider_build(const float trans[3], const float rot_deg[3], const float scale[3],
+                         float out48[48]);                       /* Scene.h:28-38      */
+void  rvh_collider_translate(float collider48[48], const float translation[3]); /* Scene.cpp:110-120 */
+float rvh_wind_fbm(float total_time);                            /* compute.comp:83-121,152 */
+int   rvh_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,501 @@
+// rvh_api.cu -- the extern "C" layer of librvh.so (see include/rvh.h for the contract and
+// the reference call site each entry point replaces).  No CPU fallback: every compute
+// entry point launches sm_100a kernels on the context's stream or fails.
+#include "../../include/rvh.h"
+#include "rvh_kernels.cuh"
+#include "rvh_host_math.h"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rvh;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL, loaded lazily so single-GPU users need no NCCL at all ---------------------
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = { "libnccl.so.2", "libnccl.so" };
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+        GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (int (*)(NcclComm*, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl lacks a required symbol"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclInt64 = 4, kNcclSum = 0;
+
+enum { EV_K1 = 0, EV_K2, EV_AR, EV_CLEAR, EV_COUNT };
+
+}  // namespace
+
+struct rvh_ctx {
+    rvh_config cfg;
+    int S = 0, S_pad = 0, N = 0, V = 1;
+    cudaStream_t stream = nullptr;
+    float* planes = nullptr;              // [6][N][S_pad]
+    float* corr = nullptr;                // [3][N][S_pad] (RVH_KEEP_CORRECTION)
+    unsigned long long* grid = nullptr;   // [G^3][4] int64
+    size_t grid_bytes = 0;
+    int* perm = nullptr;                  // internal -> external strand index (Morton order)
+    void* aos_dev = nullptr;              // Strand[S] staging / interop target
+    size_t aos_bytes = 0;
+    void* interop_aos = nullptr;          // imported VkBuffer memory (rvh_import_strands_fd)
+    cudaExternalMemory_t interop_mem = nullptr;
+    void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
+    unsigned* sort_keys = nullptr; unsigned* sort_keys_out = nullptr; int* sort_ids = nullptr;
+    StepParams P;
+    bool uploaded = false, colliders_set = false;
+    // multi-GPU
+    int rank = 0, nranks = 1;
+    NcclComm comm = nullptr;
+    // timing
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    float last_ms = 0.f;
+    bool profiling = false;
+    std::vector<cudaEvent_t> pev;         // pairs, recycled
+    std::vector<int> pev_kind; size_t pev_used = 0;
+    float prof_ms[EV_COUNT] = { 0, 0, 0, 0 };
+    int prof_n[EV_COUNT] = { 0, 0, 0, 0 };
+    long long launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(rvh_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                            \
+    do { cudaError_t e_ = (call);                                                           \
+         if (e_ != cudaSuccess)                                                             \
+             return fail(ctx, RVH_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+void prof_begin(rvh_ctx* c, int kind) {
+    if (!c->profiling) return;
+    if (c->pev_used + 2 > c->pev.size()) {
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        c->pev.push_back(a); c->pev.push_back(b); c->pev_kind.push_back(kind);
+    }
+    c->pev_kind[c->pev_used / 2] = kind;
+    cudaEventRecord(c->pev[c->pev_used], c->stream);
+}
+void prof_end(rvh_ctx* c) {
+    if (!c->profiling) return;
+    cudaEventRecord(c->pev[c->pev_used + 1], c->stream);
+    c->pev_used += 2;
+}
+void prof_collect(rvh_ctx* c) {   // caller has synchronised the stream
+    for (size_t i = 0; i + 2 <= c->pev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]) == cudaSuccess) {
+            c->prof_ms[c->pev_kind[i / 2]] += ms; c->prof_n[c->pev_kind[i / 2]] += 1;
+        }
+    }
+    c->pev_used = 0;
+}
+
+template <int V, bool GRID, bool WIND>
+void launch_k1(rvh_ctx* c) {
+    const int threads = (c->S_pad + V - 1) / V;
+    const int blocks = (threads + kBlock - 1) / kBlock;
+    k_ftl_step<V, GRID, WIND><<<blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->grid);
+}
+template <int V>
+void launch_k1_v(rvh_ctx* c, bool grid, bool wind) {
+    if (grid) { if (wind) launch_k1<V, true, true>(c); else launch_k1<V, true, false>(c); }
+    else      { if (wind) launch_k1<V, false, true>(c); else launch_k1<V, false, false>(c); }
+}
+
+int do_step(rvh_ctx* ctx, float dt, float total_time, int phases) {
+    if (!ctx->uploaded) return fail(ctx, RVH_ERR_STATE, "rvh_step before rvh_upload_strands_aos");
+    if (!ctx->colliders_set) return fail(ctx, RVH_ERR_STATE, "rvh_step before rvh_set_colliders");
+    if (!(dt > 0.f)) return fail(ctx, RVH_ERR_INVALID, "dt must be > 0");
+    StepParams& P = ctx->P;
+    P.dt = dt; P.inv_dt = 1.0f / dt; P.dt2 = dt * dt; P.vel_scale = P.damping / dt;
+    const int flags = ctx->cfg.flags;
+    const bool grid = flags & RVH_GRID_ON, wind = flags & (RVH_WIND_A | RVH_WIND_B);
+    P.wind_mode = (flags & RVH_WIND_B) ? 2 : ((flags & RVH_WIND_A) ? 1 : 0);
+    if (wind) {
+        P.wind_s2T = 2.0f * std::sin(total_time * 2.0f);
+        P.wind_T3 = total_time * 3.0f;
+        P.wind_amp = (P.wind_mode == 2) ? 7.0f * wind_fbm(total_time) : 10.0f;
+    }
+    if (phases & 1) {
+        if (grid) {
+            prof_begin(ctx, EV_CLEAR);
+            CU(cudaMemsetAsync(ctx->grid, 0, ctx->grid_bytes, ctx->stream));   // Renderer.cpp:2063
+            prof_end(ctx);
+        }
+        prof_begin(ctx, EV_K1);
+        switch (ctx->V) {
+            case 4: launch_k1_v<4>(ctx, grid, wind); break;
+            case 2: launch_k1_v<2>(ctx, grid, wind); break;
+            default: launch_k1_v<1>(ctx, grid, wind); break;
+        }
+        prof_end(ctx);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+        if (grid && ctx->nranks > 1) {
+            prof_begin(ctx, EV_AR);
+            int r = g_nccl.AllReduce(ctx->grid, ctx->grid, ctx->grid_bytes / 8, kNcclInt64, kNcclSum, ctx->comm, ctx->stream);
+            prof_end(ctx);
+            if (r != 0) return fail(ctx, RVH_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+        }
+    }
+    if ((phases & 2) && grid) {
+        prof_begin(ctx, EV_K2);
+        const size_t total = (size_t)(ctx->N - 1) * ctx->S_pad;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 64);
+        k_grid_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->P, ctx->planes, (const long long*)ctx->grid);
+        prof_end(ctx);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+    }
+    if (ctx->interop_aos) {
+        const int tiles = (ctx->S + kTile - 1) / kTile;
+        const size_t sm = (size_t)9 * ctx->N * (kTile + 1) * sizeof(float);
+        k_pack_aos<<<tiles, 256, sm, ctx->stream>>>((float4*)ctx->interop_aos, ctx->planes, ctx->corr, ctx->perm, ctx->S, ctx->S_pad, ctx->N);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+    }
+    return RVH_OK;
+}
+
+int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, const void* uid) {
+    rvh_ctx* ctx = nullptr;   // for CU(): errors go to g_create_error
+    if (!out || !cfg) return fail(nullptr, RVH_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->num_strands < 1 || cfg->num_points < 2) return fail(nullptr, RVH_ERR_INVALID, "need num_strands >= 1 and num_points >= 2");
+    if (cfg->grid_dim < 2 || cfg->grid_dim > 1024) return fail(nullptr, RVH_ERR_INVALID, "grid_dim out of range");
+    if ((size_t)cfg->num_strands * cfg->num_points > ((size_t)1 << 31)) return fail(nullptr, RVH_ERR_INVALID, "S*N too large for one context");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, RVH_ERR_CUDA, std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, RVH_ERR_INVALID, "bad device ordinal");
+    CU(cudaSetDevice(cfg->device));
+
+    rvh_ctx* c = new rvh_ctx();
+    c->cfg = *cfg;
+    c->S = cfg->num_strands; c->N = cfg->num_points;
+    c->S_pad = ((c->S + 127) / 128) * 128;
+    c->rank = rank; c->nranks = nranks;
+    int V = cfg->strands_per_thread;
+    if (V != 1 && V != 2 && V != 4) V = c->S >= 262144 ? 4 : (c->S >= 65536 ? 2 : 1);
+    c->V = V;
+    ctx = c;
+#define CUC(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e2_); rvh_destroy(c); return fail(nullptr, RVH_ERR_CUDA, m_); } } while (0)
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t plane = (size_t)c->N * c->S_pad * sizeof(float);
+    CUC(cudaMalloc(&c->planes, 6 * plane));
+    CUC(cudaMemsetAsync(c->planes, 0, 6 * plane, c->stream));
+    if (cfg->flags & RVH_KEEP_CORRECTION) {
+        CUC(cudaMalloc(&c->corr, 3 * plane));
+        CUC(cudaMemsetAsync(c->corr, 0, 3 * plane, c->stream));
+    }
+    const size_t G = cfg->grid_dim;
+    c->grid_bytes = G * G * G * 4 * sizeof(long long);
+    CUC(cudaMalloc(&c->grid, c->grid_bytes));
+    CUC(cudaMemsetAsync(c->grid, 0, c->grid_bytes, c->stream));
+    c->aos_bytes = (size_t)c->S * 48 * c->N;
+    CUC(cudaMalloc(&c->aos_dev, c->aos_bytes));
+    CUC(cudaEventCreate(&c->ev_a)); CUC(cudaEventCreate(&c->ev_b));
+    CUC(cudaFuncSetAttribute(k_unpack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * c->N * (kTile + 1) * (int)sizeof(float)));
+    CUC(cudaFuncSetAttribute(k_pack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * c->N * (kTile + 1) * (int)sizeof(float)));
+
+    StepParams& P = c->P;
+    std::memset(&P, 0, sizeof P);
+    P.S = c->S; P.S_pad = c->S_pad; P.N = c->N;
+    P.rest = cfg->rest_length; P.gravity_y = cfg->gravity_y; P.damping = cfg->damping;
+    P.vmax = cfg->vmax; P.vmax2 = cfg->vmax * cfg->vmax; P.penalty_k = cfg->penalty_k;
+    P.sphere_r = cfg->sphere_radius; P.sphere_r2 = cfg->sphere_radius * cfg->sphere_radius;
+    P.G = cfg->grid_dim; P.h = cfg->grid_extent / (float)cfg->grid_dim;    // compute.comp:205
+    for (int k = 0; k < 3; ++k) P.origin[k] = cfg->grid_origin[k];
+    P.scale = cfg->grid_scale; P.friction = cfg->friction;
+    P.int32_wrap = (cfg->flags & RVH_GRID_INT32_WRAP) ? 1 : 0;
+    P.keep_corr = c->corr ? 1 : 0;
+
+    if (nranks > 1) {
+        std::string err;
+        if (!g_nccl.load(err)) { rvh_destroy(c); return fail(nullptr, RVH_ERR_NCCL, err); }
+        NcclId id; std::memcpy(&id, uid, sizeof id);
+        int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+        if (r != 0) { rvh_destroy(c); return fail(nullptr, RVH_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error")); }
+    }
+    CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+    *out = c;
+    return RVH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rvh_abi_version(void) { return 1; }
+
+void rvh_default_config(rvh_config* cfg, int num_strands, int num_points) {
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->device = 0;
+    cfg->num_strands = num_strands; cfg->num_points = num_points;
+    cfg->rest_length = 2.5f / ((float)num_points - 1.0f);
+    cfg->gravity_y = -9.8f; cfg->damping = 0.998f; cfg->vmax = 10.0f; cfg->penalty_k = 1900.0f;
+    cfg->sphere_radius = 1.0f;
+    cfg->grid_dim = 64; cfg->grid_extent = 7.0f;
+    cfg->grid_origin[0] = -3.0f; cfg->grid_origin[1] = -2.0f; cfg->grid_origin[2] = -5.0f;
+    cfg->grid_scale = 1000000.0f; cfg->friction = 0.08f;
+    cfg->flags = RVH_GRID_ON;
+    cfg->strands_per_thread = 0;
+}
+
+int rvh_create(rvh_ctx** out, const rvh_config* cfg) { return create_impl(out, cfg, 0, 1, nullptr); }
+
+int rvh_nccl_unique_id(void* out128) {
+    std::string err;
+    if (!out128) return fail(nullptr, RVH_ERR_INVALID, "null argument");
+    if (!g_nccl.load(err)) return fail(nullptr, RVH_ERR_NCCL, err);
+    NcclId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return fail(nullptr, RVH_ERR_NCCL, "ncclGetUniqueId failed");
+    std::memcpy(out128, &id, sizeof id);
+    return RVH_OK;
+}
+
+int rvh_create_sharded(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, const void* uid) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, RVH_ERR_INVALID, "bad rank / nranks");
+    if (nranks > 1 && !uid) return fail(nullptr, RVH_ERR_INVALID, "nccl_unique_id required when nranks > 1");
+    return create_impl(out, cfg, rank, nranks, uid);
+}
+
+int rvh_set_colliders(rvh_ctx* ctx, const void* colliders, int n) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (n < 0 || n > 1 + kMaxEllipsoids || (n > 0 && !colliders)) return fail(ctx, RVH_ERR_INVALID, "0 <= n <= 8 colliders of 192 bytes");
+    const float* c = (const float*)colliders;
+    StepParams& P = ctx->P;
+    P.has_sphere = n > 0; P.n_ell = n > 0 ? n - 1 : 0;
+    if (n > 0) { P.sphere_c[0] = c[12]; P.sphere_c[1] = c[13]; P.sphere_c[2] = c[14]; }   // transform[3].xyz, compute.comp:162
+    for (int j = 1; j < n; ++j) {
+        const float* X = c + 48 * j; const float* I = X + 16; const float* IT = X + 32;
+        Ellipsoid& E = P.ell[j - 1];
+        for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < 4; ++k) { E.inv[r * 4 + k] = I[k * 4 + r]; E.xf[r * 4 + k] = X[k * 4 + r]; }
+        for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < 3; ++k) E.nt[r * 3 + k] = IT[k * 4 + r];
+    }
+    ctx->colliders_set = true;
+    return RVH_OK;
+}
+
+static int unpack_from_staging(rvh_ctx* ctx) {
+    const bool reorder = !(ctx->cfg.flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
+    if (reorder) {
+        if (!ctx->perm) {
+            CU(cudaMalloc(&ctx->perm, sizeof(int) * ctx->S));
+            CU(cudaMalloc(&ctx->sort_keys, sizeof(unsigned) * ctx->S));
+            CU(cudaMalloc(&ctx->sort_keys_out, sizeof(unsigned) * ctx->S));
+            CU(cudaMalloc(&ctx->sort_ids, sizeof(int) * ctx->S));
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, ctx->sort_tmp_bytes, ctx->sort_keys, ctx->sort_keys_out, ctx->sort_ids, ctx->perm, ctx->S, 0, 30, ctx->stream));
+            CU(cudaMalloc(&ctx->sort_tmp, ctx->sort_tmp_bytes));
+        }
+        k_morton_keys<<<(ctx->S + 255) / 256, 256, 0, ctx->stream>>>((const float4*)ctx->aos_dev, ctx->S, ctx->N, ctx->P.origin[0], ctx->P.origin[1], ctx->P.origin[2],
+                                                                     1.0f / ctx->cfg.grid_extent, ctx->sort_keys, ctx->sort_ids);
+        CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, ctx->sort_tmp_bytes, ctx->sort_keys, ctx->sort_keys_out, ctx->sort_ids, ctx->perm, ctx->S, 0, 30, ctx->stream));
+    }
+    const int tiles = ctx->S_pad / kTile;
+    const size_t sm = (size_t)6 * ctx->N * (kTile + 1) * sizeof(float);
+    k_unpack_aos<<<tiles, 256, sm, ctx->stream>>>((const float4*)ctx->aos_dev, ctx->planes, reorder ? ctx->perm : nullptr, ctx->S, ctx->S_pad, ctx->N, ctx->P.rest);
+    CU(cudaGetLastError());
+    ctx->launches += reorder ? 3 : 1;
+    ctx->uploaded = true;
+    return RVH_OK;
+}
+
+static int pack_to_staging(rvh_ctx* ctx) {
+    const int tiles = (ctx->S + kTile - 1) / kTile;
+    const size_t sm = (size_t)9 * ctx->N * (kTile + 1) * sizeof(float);
+    const bool reorder = ctx->perm != nullptr && !(ctx->cfg.flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
+    k_pack_aos<<<tiles, 256, sm, ctx->stream>>>((float4*)ctx->aos_dev, ctx->planes, ctx->corr, reorder ? ctx->perm : nullptr, ctx->S, ctx->S_pad, ctx->N);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return RVH_OK;
+}
+
+int rvh_upload_strands_aos(rvh_ctx* ctx, const void* strands, size_t bytes) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!strands || bytes != ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "strands must be S*48*N bytes");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(ctx->aos_dev, strands, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return unpack_from_staging(ctx);
+}
+
+int rvh_download_strands_aos(rvh_ctx* ctx, void* strands, size_t bytes) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!strands || bytes != ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "strands must be S*48*N bytes");
+    if (!ctx->uploaded) return fail(ctx, RVH_ERR_STATE, "nothing uploaded");
+    CU(cudaSetDevice(ctx->cfg.device));
+    int r = pack_to_staging(ctx);
+    if (r) return r;
+    CU(cudaMemcpyAsync(strands, ctx->aos_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RVH_OK;
+}
+
+int rvh_import_strands_fd(rvh_ctx* ctx, int fd, size_t bytes) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (bytes < ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "imported buffer smaller than Strand[S]");
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaExternalMemoryHandleDesc hd; std::memset(&hd, 0, sizeof hd);
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd; hd.handle.fd = fd; hd.size = bytes;
+    CU(cudaImportExternalMemory(&ctx->interop_mem, &hd));
+    cudaExternalMemoryBufferDesc bd; std::memset(&bd, 0, sizeof bd);
+    bd.offset = 0; bd.size = bytes;
+    CU(cudaExternalMemoryGetMappedBuffer(&ctx->interop_aos, ctx->interop_mem, &bd));
+    return RVH_OK;
+}
+
+int rvh_step(rvh_ctx* ctx, float dt, float total_time) {
+    if (!ctx) return RVH_ERR_INVALID;
+    CU(cudaSetDevice(ctx->cfg.device));
+    return do_step(ctx, dt, total_time, 3);
+}
+
+int rvh_step_phases(rvh_ctx* ctx, float dt, float total_time, int phases) {
+    if (!ctx) return RVH_ERR_INVALID;
+    CU(cudaSetDevice(ctx->cfg.device));
+    return do_step(ctx, dt, total_time, phases);
+}
+
+int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (n < 1) return fail(ctx, RVH_ERR_INVALID, "n must be >= 1");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (ms_out) CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+    float t = total_time0;
+    for (int i = 0; i < n; ++i) {
+        int r = do_step(ctx, dt, t, 3);
+        if (r) return r;
+        t += dt;
+    }
+    if (ms_out) {
+        CU(cudaEventRecord(ctx->ev_b, ctx->stream));
+        CU(cudaEventSynchronize(ctx->ev_b));
+        CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev_a, ctx->ev_b));
+        *ms_out = ctx->last_ms;
+        ctx->last_ms /= (float)n;
+        prof_collect(ctx);
+    }
+    return RVH_OK;
+}
+
+int rvh_step_host(rvh_ctx* ctx, void* strands, size_t bytes, float dt, float total_time) {
+    int r = rvh_upload_strands_aos(ctx, strands, bytes);
+    if (r) return r;
+    r = do_step(ctx, dt, total_time, 3);
+    if (r) return r;
+    return rvh_download_strands_aos(ctx, strands, bytes);
+}
+
+int rvh_download_grid(rvh_ctx* ctx, void* cells, size_t bytes) {
+    if (!ctx) return RVH_ERR_INVALID;
+    const bool wrap = ctx->cfg.flags & RVH_GRID_INT32_WRAP;
+    const size_t want = wrap ? ctx->grid_bytes / 2 : ctx->grid_bytes;
+    if (!cells || bytes != want) return fail(ctx, RVH_ERR_INVALID, "grid download size mismatch");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (!wrap) {
+        CU(cudaMemcpyAsync(cells, ctx->grid, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    } else {
+        std::vector<long long> tmp(ctx->grid_bytes / 8);
+        CU(cudaMemcpyAsync(tmp.data(), ctx->grid, ctx->grid_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        int32_t* o = (int32_t*)cells;
+        for (size_t i = 0; i < tmp.size(); ++i) o[i] = (int32_t)(uint32_t)(uint64_t)tmp[i];
+    }
+    return RVH_OK;
+}
+
+int rvh_draw_indirect(rvh_ctx* ctx, uint32_t out[4]) {
+    if (!ctx || !out) return RVH_ERR_INVALID;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    // compute.comp:126-130,302 count invocations; the reference leaves 32*ceil(S/32) here because
+    // the shader has no bounds guard.  This path reports the strand count Hair::Hair set (Strand.cpp:178-182).
+    out[0] = (uint32_t)ctx->S; out[1] = 1; out[2] = 0; out[3] = 0;
+    return RVH_OK;
+}
+
+int rvh_profile_enable(rvh_ctx* ctx, int on) {
+    if (!ctx) return RVH_ERR_INVALID;
+    ctx->profiling = on != 0;
+    return RVH_OK;
+}
+
+int rvh_profile_read(rvh_ctx* ctx, float ms[4], int launches[4]) {
+    if (!ctx) return RVH_ERR_INVALID;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    prof_collect(ctx);
+    for (int i = 0; i < EV_COUNT; ++i) {
+        if (ms) ms[i] = ctx->prof_ms[i];
+        if (launches) launches[i] = ctx->prof_n[i];
+        ctx->prof_ms[i] = 0.f; ctx->prof_n[i] = 0;
+    }
+    return RVH_OK;
+}
+
+int rvh_sync(rvh_ctx* ctx) {
+    if (!ctx) return RVH_ERR_INVALID;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RVH_OK;
+}
+
+float rvh_last_step_ms(rvh_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
+long long rvh_kernel_launches(rvh_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* rvh_last_error(rvh_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void rvh_destroy(rvh_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->interop_aos) cudaFree(c->interop_aos);
+    if (c->interop_mem) cudaDestroyExternalMemory(c->interop_mem);
+    cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->perm); cudaFree(c->aos_dev);
+    cudaFree(c->sort_tmp); cudaFree(c->sort_keys); cudaFree(c->sort_keys_out); cudaFree(c->sort_ids);
+    for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void rvh_collider_build(const float t[3], const float r[3], const float s[3], float out48[48]) { collider_build(t, r, s, out48); }
+void rvh_collider_translate(float c48[48], const float tr[3]) { collider_translate(c48, tr); }
+float rvh_wind_fbm(float total_time) { return wind_fbm(total_time); }
+
+}  // extern "C"

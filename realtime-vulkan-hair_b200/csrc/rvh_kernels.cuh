@@ -1,0 +1,414 @@
+// rvh_kernels.cuh -- sm_100a kernels of the guide-strand physics step.
+//
+// Device-side replacement for src/shaders/compute.comp (file:line below are relative to
+// the reference tree).  Layout in HBM is point-major SoA ("planes"):
+//     planes[k][i][s]   k in {px,py,pz,vx,vy,vz}, i = point on strand, s = strand
+// so that a warp reading point i of 32*V consecutive strands issues fully coalesced
+// 32/64/128-bit loads per plane, and the root->tip chain of a strand lives in registers.
+// The voxel grid is int64 [G^3][4] (vx,vy,vz,density), fixed point x grid_scale; integer
+// accumulation makes the result independent of atomics order and of the GPU count.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rvh {
+
+constexpr int kMaxEllipsoids = 7;       // colliders 1..7; collider 0 is the sphere
+constexpr int kBlock = 128;
+
+struct Ellipsoid {
+    float inv[12];   // rows 0..2 of Collider::inv      : q = inv * (p,1)     compute.comp:64-67
+    float xf[12];    // rows 0..2 of Collider::transform: on = xf * (nq,1)    compute.comp:76-79
+    float nt[9];     // upper 3x3 of Collider::invTrans : n = nt * q          compute.comp:70-73
+};
+
+struct StepParams {
+    int S, S_pad, N;
+    float rest, gravity_y, damping, vmax, vmax2, penalty_k;
+    float sphere_r, sphere_r2, sphere_c[3];
+    int has_sphere, n_ell;
+    Ellipsoid ell[kMaxEllipsoids];
+    int G;
+    float h, origin[3], scale, friction;
+    float dt, inv_dt, dt2, vel_scale;      // vel_scale = damping / dt
+    int wind_mode;                          // 0 off, 1 = variant A (:151), 2 = variant B (:152)
+    float wind_s2T, wind_T3, wind_amp;      // 2*sin(2T); 3T; 10 (A) or 7*fbm(sinT,cosT) (B)
+    int int32_wrap, keep_corr;
+};
+
+template <int V> struct VecOf;
+template <> struct VecOf<1> { using type = float; };
+template <> struct VecOf<2> { using type = float2; };
+template <> struct VecOf<4> { using type = float4; };
+
+template <int V> __device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&o)[V]) {
+    if constexpr (V == 1) { o[0] = __ldg(p); }
+    else if constexpr (V == 2) { float2 t = __ldg(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1] = t.y; }
+    else { float4 t = __ldg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+}
+template <int V> __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&o)[V]) {
+    if constexpr (V == 1) { *p = o[0]; }
+    else if constexpr (V == 2) { *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1]); }
+    else { *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]); }
+}
+
+// ---- per-axis cell range of a point: compute.comp:219-229 --------------------------------
+// The shader's [max(floor,0), min(floor+1,G-1)] range is exactly "cells f and f+1, each kept
+// only if it lies in [0,G-1]"; w0/w1 are clamp(1-|g-cell|,0,1) (compute.comp:237-239).
+struct AxisCells { int f; float w0, w1; bool ok0, ok1; };
+
+__device__ __forceinline__ AxisCells axis_cells(float p, float origin, float h, int G) {
+    AxisCells a;
+    const float g = __fdiv_rn(p - origin, h);
+    float fl = floorf(g);
+    fl = fminf(fmaxf(fl, -2.0f), (float)G);           // far-away / NaN points touch no cell
+    a.f = (int)fl;
+    a.w0 = __saturatef(1.0f - fabsf(g - (float)a.f));
+    a.w1 = __saturatef(1.0f - fabsf(g - (float)(a.f + 1)));
+    a.ok0 = (a.f >= 0) && (a.f <= G - 1);
+    a.ok1 = (a.f + 1 >= 0) && (a.f + 1 <= G - 1);
+    return a;
+}
+
+// ---- P2 splat of one point: compute.comp:231-252 ------------------------------------------
+__device__ __forceinline__ void splat_point(const StepParams& P, unsigned long long* __restrict__ grid,
+                                            float px, float py, float pz, float vx, float vy, float vz) {
+    const AxisCells X = axis_cells(px, P.origin[0], P.h, P.G);
+    const AxisCells Y = axis_cells(py, P.origin[1], P.h, P.G);
+    const AxisCells Z = axis_cells(pz, P.origin[2], P.h, P.G);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        if (!(a ? X.ok1 : X.ok0)) continue;
+        const float xw = a ? X.w1 : X.w0;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            if (!(b ? Y.ok1 : Y.ok0)) continue;
+            const float xyw = __fmul_rn(xw, b ? Y.w1 : Y.w0);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (!(c ? Z.ok1 : Z.ok0)) continue;
+                const float tw = __fmul_rn(xyw, c ? Z.w1 : Z.w0);
+                const int idx = (X.f + a) + (Y.f + b) * P.G + (Z.f + c) * P.G * P.G;
+                // int(SCALE * weightedVelocity.k), int(SCALE * totalWeight): truncation toward zero
+                const int c0 = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vx)));
+                const int c1 = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vy)));
+                const int c2 = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vz)));
+                const int c3 = __float2int_rz(__fmul_rn(P.scale, tw));
+                unsigned long long* cell = grid + 4 * (size_t)idx;
+                if (c0) atomicAdd(cell + 0, (unsigned long long)(long long)c0);
+                if (c1) atomicAdd(cell + 1, (unsigned long long)(long long)c1);
+                if (c2) atomicAdd(cell + 2, (unsigned long long)(long long)c2);
+                if (c3) atomicAdd(cell + 3, (unsigned long long)(long long)c3);
+            }
+        }
+    }
+}
+
+// ---- P3 gather of one point: compute.comp:259-297 ------------------------------------------
+// Written without FMA contraction so the result is bit-identical to the C oracle when
+// positions, velocities and grid are.
+__device__ __forceinline__ void gather_point(const StepParams& P, const long long* __restrict__ grid,
+                                             float px, float py, float pz, float& vx, float& vy, float& vz) {
+    const AxisCells X = axis_cells(px, P.origin[0], P.h, P.G);
+    const AxisCells Y = axis_cells(py, P.origin[1], P.h, P.G);
+    const AxisCells Z = axis_cells(pz, P.origin[2], P.h, P.G);
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        if (!(a ? X.ok1 : X.ok0)) continue;
+        const float xw = a ? X.w1 : X.w0;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            if (!(b ? Y.ok1 : Y.ok0)) continue;
+            const float xyw = __fmul_rn(xw, b ? Y.w1 : Y.w0);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (!(c ? Z.ok1 : Z.ok0)) continue;
+                const float tw = __fmul_rn(xyw, c ? Z.w1 : Z.w0);
+                const int idx = (X.f + a) + (Y.f + b) * P.G + (Z.f + c) * P.G * P.G;
+                const longlong2* cell = reinterpret_cast<const longlong2*>(grid + 4 * (size_t)idx);
+                const longlong2 v01 = __ldg(cell), v2d = __ldg(cell + 1);
+                long long dens = v2d.y, v0 = v01.x, v1 = v01.y, v2 = v2d.x;
+                if (P.int32_wrap) { dens = (int)dens; v0 = (int)v0; v1 = (int)v1; v2 = (int)v2; }
+                if (dens > 0) {
+                    const float s = __fmul_rn(tw, __frcp_rn(__ll2float_rn(dens)));
+                    gx = __fadd_rn(gx, __fmul_rn(s, __ll2float_rn(v0)));
+                    gy = __fadd_rn(gy, __fmul_rn(s, __ll2float_rn(v1)));
+                    gz = __fadd_rn(gz, __fmul_rn(s, __ll2float_rn(v2)));
+                }
+            }
+        }
+    }
+    const float fr = P.friction, omf = __fsub_rn(1.0f, fr);
+    vx = __fadd_rn(__fmul_rn(omf, vx), __fmul_rn(fr, gx));
+    vy = __fadd_rn(__fmul_rn(omf, vy), __fmul_rn(fr, gy));
+    vz = __fadd_rn(__fmul_rn(omf, vz), __fmul_rn(fr, gz));
+}
+
+// ---- P1 for one point: compute.comp:144-201 -------------------------------------------------
+struct PointOut { float px, py, pz, vx, vy, vz, dx, dy, dz; };
+
+template <bool WIND>
+__device__ __forceinline__ PointOut point_update(const StepParams& P, float cx, float cy, float cz,
+                                                 float vx, float vy, float vz,
+                                                 float parx, float pary, float parz) {
+    float fx = 0.0f, fy = P.gravity_y, fz = 0.0f;                       // :150
+    if (WIND) {
+        const float wx = P.wind_s2T * cosf(cy * 10.0f) * sinf((cy + 5.0f) * 15.0f);
+        if (P.wind_mode == 1) {                                         // :151
+            const float cl = fminf(fmaxf(cy * 2.0f, 0.2f), 2.0f);
+            fx = fmaf(P.wind_amp, wx, fx);
+            fz = fmaf(P.wind_amp, -cl, fz);
+        } else {                                                        // :152
+            fx = fmaf(P.wind_amp, wx, fx);
+            fy = fmaf(P.wind_amp, 4.0f * sinf(fmaf(cz, 5.0f, P.wind_T3)), fy);
+            fz = fmaf(P.wind_amp, -0.6f * (cy + 3.0f), fz);
+        }
+    }
+
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    int hits = 0;
+    if (P.has_sphere) {                                                 // :160-169
+        const float dx = cx - P.sphere_c[0], dy = cy - P.sphere_c[1], dz = cz - P.sphere_c[2];
+        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        if (d2 < P.sphere_r2) {
+            const float rinv = rsqrtf(d2);
+            const float dist = d2 * rinv;
+            const float s = P.penalty_k * (P.sphere_r - dist) * rinv;
+            ax = s * dx; ay = s * dy; az = s * dz;
+            hits = 1;
+        }
+    }
+#pragma unroll 1
+    for (int j = 0; j < P.n_ell; ++j) {                                 // :170-179
+        const Ellipsoid& E = P.ell[j];
+        const float qx = fmaf(E.inv[0], cx, fmaf(E.inv[1], cy, fmaf(E.inv[2], cz, E.inv[3])));
+        const float qy = fmaf(E.inv[4], cx, fmaf(E.inv[5], cy, fmaf(E.inv[6], cz, E.inv[7])));
+        const float qz = fmaf(E.inv[8], cx, fmaf(E.inv[9], cy, fmaf(E.inv[10], cz, E.inv[11])));
+        const float q2 = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
+        if (q2 <= 1.0f) {
+            const float rq = rsqrtf(q2);
+            const float ux = qx * rq, uy = qy * rq, uz = qz * rq;
+            const float ox = fmaf(E.xf[0], ux, fmaf(E.xf[1], uy, fmaf(E.xf[2], uz, E.xf[3])));
+            const float oy = fmaf(E.xf[4], ux, fmaf(E.xf[5], uy, fmaf(E.xf[6], uz, E.xf[7])));
+            const float oz = fmaf(E.xf[8], ux, fmaf(E.xf[9], uy, fmaf(E.xf[10], uz, E.xf[11])));
+            const float ex = cx - ox, ey = cy - oy, ez = cz - oz;
+            const float d = sqrtf(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
+            float nx = fmaf(E.nt[0], qx, fmaf(E.nt[1], qy, E.nt[2] * qz));
+            float ny = fmaf(E.nt[3], qx, fmaf(E.nt[4], qy, E.nt[5] * qz));
+            float nz = fmaf(E.nt[6], qx, fmaf(E.nt[7], qy, E.nt[8] * qz));
+            const float s = P.penalty_k * d * rsqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+            ax = fmaf(s, nx, ax); ay = fmaf(s, ny, ay); az = fmaf(s, nz, az);
+            ++hits;
+        }
+    }
+    if (hits > 0) {                                                     // :182-184
+        const float ih = __frcp_rn((float)hits);
+        fx = fmaf(ax, ih, fx); fy = fmaf(ay, ih, fy); fz = fmaf(az, ih, fz);
+    }
+
+    PointOut o;
+    const float prx = fmaf(P.dt2, fx, fmaf(P.dt, vx, cx));              // :187
+    const float pry = fmaf(P.dt2, fy, fmaf(P.dt, vy, cy));
+    const float prz = fmaf(P.dt2, fz, fmaf(P.dt, vz, cz));
+    const float ddx = prx - parx, ddy = pry - pary, ddz = prz - parz;   // :191-192
+    const float sc = P.rest * rsqrtf(fmaf(ddx, ddx, fmaf(ddy, ddy, ddz * ddz)));
+    o.px = fmaf(sc, ddx, parx); o.py = fmaf(sc, ddy, pary); o.pz = fmaf(sc, ddz, parz);
+    float nvx = (o.px - cx) * P.vel_scale, nvy = (o.py - cy) * P.vel_scale, nvz = (o.pz - cz) * P.vel_scale;  // :195-197
+    const float l2 = fmaf(nvx, nvx, fmaf(nvy, nvy, nvz * nvz));
+    if (l2 > P.vmax2) {                                                 // :198-200
+        const float s = P.vmax * rsqrtf(l2);
+        nvx *= s; nvy *= s; nvz *= s;
+    }
+    o.vx = nvx; o.vy = nvy; o.vz = nvz;
+    o.dx = P.damping * (o.px - prx); o.dy = P.damping * (o.py - pry); o.dz = P.damping * (o.pz - prz);  // :201
+    return o;
+}
+
+// ---- K1: integrate + collide + FTL + corrected velocity (+ splat) -------------------------
+// One thread owns V consecutive strands and walks them root->tip together (V independent
+// dependency chains per thread).  Point i's velocity is final only once d_{i+1} is known
+// (compute.comp:213-215), so velocity store and splat trail the position by one point.
+template <int V, bool GRID, bool WIND>
+__global__ void __launch_bounds__(kBlock)
+k_ftl_step(const StepParams P, float* __restrict__ planes, float* __restrict__ corr,
+           unsigned long long* __restrict__ grid) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s0 = t * V;
+    if (s0 >= P.S_pad) return;
+    const size_t plane = (size_t)P.N * P.S_pad;
+    float* const ppx = planes + s0;
+    float* const ppy = ppx + plane;
+    float* const ppz = ppy + plane;
+    float* const pvx = ppz + plane;
+    float* const pvy = pvx + plane;
+    float* const pvz = pvy + plane;
+
+    float parx[V], pary[V], parz[V];
+    load_vec<V>(ppx, parx); load_vec<V>(ppy, pary); load_vec<V>(ppz, parz);
+    float nx[V], ny[V], nz[V], nvx[V], nvy[V], nvz[V];
+    {
+        const size_t o = P.S_pad;
+        load_vec<V>(ppx + o, nx); load_vec<V>(ppy + o, ny); load_vec<V>(ppz + o, nz);
+        load_vec<V>(pvx + o, nvx); load_vec<V>(pvy + o, nvy); load_vec<V>(pvz + o, nvz);
+    }
+    float lvx[V], lvy[V], lvz[V];   // clamped velocity of the previous point, correction pending
+
+    for (int i = 1; i < P.N; ++i) {
+        float cx[V], cy[V], cz[V], vx[V], vy[V], vz[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) { cx[u] = nx[u]; cy[u] = ny[u]; cz[u] = nz[u]; vx[u] = nvx[u]; vy[u] = nvy[u]; vz[u] = nvz[u]; }
+        if (i + 1 < P.N) {
+            const size_t o = (size_t)(i + 1) * P.S_pad;
+            load_vec<V>(ppx + o, nx); load_vec<V>(ppy + o, ny); load_vec<V>(ppz + o, nz);
+            load_vec<V>(pvx + o, nvx); load_vec<V>(pvy + o, nvy); load_vec<V>(pvz + o, nvz);
+        }
+        float opx[V], opy[V], opz[V], fvx[V], fvy[V], fvz[V], odx[V], ody[V], odz[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const PointOut o = point_update<WIND>(P, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
+            opx[u] = o.px; opy[u] = o.py; opz[u] = o.pz;
+            odx[u] = o.dx; ody[u] = o.dy; odz[u] = o.dz;
+            // finalise point i-1: v_{i-1} -= d_i / dt   (compute.comp:213-215)
+            fvx[u] = fmaf(-o.dx, P.inv_dt, lvx[u]); fvy[u] = fmaf(-o.dy, P.inv_dt, lvy[u]); fvz[u] = fmaf(-o.dz, P.inv_dt, lvz[u]);
+            lvx[u] = o.vx; lvy[u] = o.vy; lvz[u] = o.vz;
+        }
+        const size_t oi = (size_t)i * P.S_pad;
+        store_vec<V>(ppx + oi, opx); store_vec<V>(ppy + oi, opy); store_vec<V>(ppz + oi, opz);
+        if (P.keep_corr) {
+            float* c0 = corr + s0 + oi;
+            store_vec<V>(c0, odx); store_vec<V>(c0 + plane, ody); store_vec<V>(c0 + 2 * plane, odz);
+        }
+        if (i > 1) {
+            const size_t om = oi - P.S_pad;
+            store_vec<V>(pvx + om, fvx); store_vec<V>(pvy + om, fvy); store_vec<V>(pvz + om, fvz);
+            if (GRID) {
+#pragma unroll
+                for (int u = 0; u < V; ++u)
+                    if (s0 + u < P.S) splat_point(P, grid, parx[u], pary[u], parz[u], fvx[u], fvy[u], fvz[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) { parx[u] = opx[u]; pary[u] = opy[u]; parz[u] = opz[u]; }
+    }
+    // last point: no correction term (compute.comp:213 `i != NUM_CURVE_POINTS - 1`)
+    const size_t ol = (size_t)(P.N - 1) * P.S_pad;
+    store_vec<V>(pvx + ol, lvx); store_vec<V>(pvy + ol, lvy); store_vec<V>(pvz + ol, lvz);
+    if (GRID) {
+#pragma unroll
+        for (int u = 0; u < V; ++u)
+            if (s0 + u < P.S) splat_point(P, grid, parx[u], pary[u], parz[u], lvx[u], lvy[u], lvz[u]);
+    }
+}
+
+// ---- K2: grid gather + friction, one thread per point -------------------------------------
+__global__ void __launch_bounds__(256)
+k_grid_gather(const StepParams P, float* __restrict__ planes, const long long* __restrict__ grid) {
+    const size_t plane = (size_t)P.N * P.S_pad;
+    const size_t total = (size_t)(P.N - 1) * P.S_pad;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const int s = (int)(k % P.S_pad);
+        if (s >= P.S) continue;
+        const size_t o = k + P.S_pad;   // skip the root row
+        float vx = planes[3 * plane + o], vy = planes[4 * plane + o], vz = planes[5 * plane + o];
+        gather_point(P, grid, planes[o], planes[plane + o], planes[2 * plane + o], vx, vy, vz);
+        planes[3 * plane + o] = vx; planes[4 * plane + o] = vy; planes[5 * plane + o] = vz;
+    }
+}
+
+// ---- AoS <-> planes (the reference's Strand[S] vertex-buffer layout, Strand.h:11-15) -------
+// One block per tile of 32 strands; shared-memory transpose so both sides are coalesced.
+// perm[s_internal] = external strand index (nullptr = identity).
+constexpr int kTile = 32;
+
+__global__ void __launch_bounds__(256)
+k_unpack_aos(const float4* __restrict__ aos, float* __restrict__ planes, const int* __restrict__ perm,
+             int S, int S_pad, int N, float rest) {
+    extern __shared__ float sm[];            // [6][N][kTile+1]
+    const int tile0 = blockIdx.x * kTile;
+    const int q2 = 2 * N;
+    for (int k = threadIdx.x; k < kTile * q2; k += blockDim.x) {
+        const int sl = k / q2, q = k % q2;
+        const int s = tile0 + sl;
+        float4 v;
+        if (s < S) {
+            const size_t e = perm ? (size_t)perm[s] : (size_t)s;
+            v = aos[e * 3 * N + q];
+        } else {
+            // padding strand: straight, at rest spacing, far outside the grid and colliders
+            const int j = q < N ? q : q - N;
+            v = q < N ? make_float4(1.0e4f + rest * j, 1.0e4f, 1.0e4f, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int j = q < N ? q : q - N;
+        const int kb = q < N ? 0 : 3;
+        sm[((kb + 0) * N + j) * (kTile + 1) + sl] = v.x;
+        sm[((kb + 1) * N + j) * (kTile + 1) + sl] = v.y;
+        sm[((kb + 2) * N + j) * (kTile + 1) + sl] = v.z;
+    }
+    __syncthreads();
+    const size_t plane = (size_t)N * S_pad;
+    for (int k = threadIdx.x; k < 6 * N * kTile; k += blockDim.x) {
+        const int sl = k % kTile, r = k / kTile;     // r = kk*N + j
+        const int kk = r / N, j = r % N;
+        if (tile0 + sl < S_pad) planes[kk * plane + (size_t)j * S_pad + tile0 + sl] = sm[r * (kTile + 1) + sl];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_aos(float4* __restrict__ aos, const float* __restrict__ planes, const float* __restrict__ corr,
+           const int* __restrict__ perm, int S, int S_pad, int N) {
+    extern __shared__ float sm[];            // [9][N][kTile+1]
+    const int tile0 = blockIdx.x * kTile;
+    const size_t plane = (size_t)N * S_pad;
+    const int nk = corr ? 9 : 6;
+    for (int k = threadIdx.x; k < nk * N * kTile; k += blockDim.x) {
+        const int sl = k % kTile, r = k / kTile;
+        const int kk = r / N, j = r % N;
+        float v = 0.f;
+        if (tile0 + sl < S_pad)
+            v = kk < 6 ? planes[kk * plane + (size_t)j * S_pad + tile0 + sl]
+                       : corr[(kk - 6) * plane + (size_t)j * S_pad + tile0 + sl];
+        sm[r * (kTile + 1) + sl] = v;
+    }
+    __syncthreads();
+    const int q3 = 3 * N;
+    for (int k = threadIdx.x; k < kTile * q3; k += blockDim.x) {
+        const int sl = k / q3, q = k % q3;
+        const int s = tile0 + sl;
+        if (s >= S) continue;
+        const int a = q / N, j = q % N;      // a: 0 curvePoints, 1 curveVels, 2 correctionVecs
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a < 2 || corr) {
+            v.x = sm[((3 * a + 0) * N + j) * (kTile + 1) + sl];
+            v.y = sm[((3 * a + 1) * N + j) * (kTile + 1) + sl];
+            v.z = sm[((3 * a + 2) * N + j) * (kTile + 1) + sl];
+        }
+        if (a == 0) v.w = 1.0f;              // curvePoints.w = 1 (Strand.cpp:165, compute.comp:196)
+        if (a == 2 && j == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);   // correctionVecs[0] is never written
+        const size_t e = perm ? (size_t)perm[s] : (size_t)s;
+        aos[e * q3 + q] = v;
+    }
+}
+
+// Morton key (10 bits per axis over the grid box) of each strand's root, for spatial ordering.
+__device__ __forceinline__ unsigned part1by2(unsigned x) {
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+__global__ void k_morton_keys(const float4* __restrict__ aos, int S, int N, float ox, float oy, float oz,
+                              float inv_extent, unsigned* __restrict__ keys, int* __restrict__ ids) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const float4 r = aos[(size_t)s * 3 * N];
+    const float fx = fminf(fmaxf((r.x - ox) * inv_extent, 0.f), 0.999999f) * 1024.f;
+    const float fy = fminf(fmaxf((r.y - oy) * inv_extent, 0.f), 0.999999f) * 1024.f;
+    const float fz = fminf(fmaxf((r.z - oz) * inv_extent, 0.f), 0.999999f) * 1024.f;
+    keys[s] = part1by2((unsigned)fx) | (part1by2((unsigned)fy) << 1) | (part1by2((unsigned)fz) << 2);
+    ids[s] = s;
+}
+
+}  // namespace rvh

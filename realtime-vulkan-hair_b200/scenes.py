@@ -1,0 +1,88 @@
+"""Scene inputs for tests and benchmarks (host side, numpy).
+
+* `reference_colliders()`  -- the six colliders of the shipped scene (main.cpp:229-237), built
+  with the library's own Collider maths (rvh_collider_build <-> Scene.h:28-38).
+* `synthetic_head(S, N, L)` -- seeded synthetic head of SURVEY.md section 8(d): roots on the top
+  hemisphere of the head ellipsoid (collider 1), counter-based splitmix64 (seed 8) keyed by the
+  GLOBAL strand id so any rank can generate exactly its shard, points at exact rest spacing.
+"""
+import numpy as np
+
+from .binding import collider_build, collider_translate
+
+# main.cpp:229-237: translation, rotation (degrees), scale
+REFERENCE_COLLIDER_TRS = [
+    ((2.0, 0.0, 1.0), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)),                       # sphere (movable)
+    ((0.0, 2.64, 0.08), (-38.270, 0.0, 0.0), (0.817, 1.158, 1.01)),            # head
+    ((0.0, 1.35, -0.288), (18.301, 0.0, 0.0), (0.457, 1.0, 0.538)),            # neck
+    ((0.0, -0.380, -0.116), (-17.260, 0.0, 0.0), (1.078, 1.683, 0.974)),       # bust
+    ((-0.698, 0.087, -0.36), (-20.254, 13.144, 34.5), (0.721, 1.0, 0.724)),    # right shoulder
+    ((0.698, 0.087, -0.36), (-20.254, 13.144, -34.5), (0.721, 1.0, 0.724)),    # left shoulder
+]
+
+
+def reference_colliders():
+    return np.stack([collider_build(t, r, s) for (t, r, s) in REFERENCE_COLLIDER_TRS]).astype(np.float32)
+
+
+def bench_colliders():
+    """Reference colliders with the sphere moved to (0.9, 2.2, 0.5) so that it intersects the hair."""
+    c = reference_colliders()
+    cur = c[0, 12:15].copy()
+    c[0] = collider_translate(c[0], np.array([0.9, 2.2, 0.5], np.float32) - cur)
+    return c
+
+
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def synthetic_head(num_strands, num_points, strand_length=2.5, first_strand=0, colliders=None, seed=8,
+                   chunk=1 << 18, out=None):
+    """Strand[S] AoS (float32 [S][3][N][4]) for global strand ids first_strand .. first_strand+S-1."""
+    if colliders is None:
+        colliders = reference_colliders()
+    head = np.asarray(colliders, np.float32).reshape(-1, 48)[1]
+    X = head[0:16].reshape(4, 4).T.astype(np.float32)          # column-major -> [row][col]
+    IT = head[32:48].reshape(4, 4).T.astype(np.float32)
+    S, N = int(num_strands), int(num_points)
+    rest = np.float32(np.float32(strand_length) / np.float32(N - 1))
+    if out is None:
+        out = np.empty((S, 3, N, 4), np.float32)
+    j = np.arange(N, dtype=np.float32)
+    old = np.seterr(over="ignore")
+    try:
+        for lo in range(0, S, chunk):
+            hi = min(S, lo + chunk)
+            sid = (np.arange(lo, hi, dtype=np.uint64) + np.uint64(first_strand))
+            base = (np.uint64(seed) << np.uint64(32)) + np.uint64(2) * sid
+            r0 = (_splitmix64(base) >> np.uint64(40)).astype(np.float32) / np.float32(1 << 24)
+            r1 = (_splitmix64(base + np.uint64(1)) >> np.uint64(40)).astype(np.float32) / np.float32(1 << 24)
+            uy = r0
+            rad = np.sqrt(np.maximum(np.float32(1.0) - uy * uy, np.float32(0.0))).astype(np.float32)
+            phi = (np.float32(2.0 * np.pi) * r1).astype(np.float32)
+            u = np.stack([rad * np.cos(phi), uy, rad * np.sin(phi)], axis=1).astype(np.float32)
+            root = (u @ X[:3, :3].T + X[:3, 3]).astype(np.float32)
+            n = (u @ IT[:3, :3].T).astype(np.float32)
+            n /= np.linalg.norm(n, axis=1, keepdims=True).astype(np.float32)
+            d = n + np.float32(0.1) * np.array([0.05, 5.0, -2.0], np.float32)
+            d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+            blk = out[lo:hi]
+            blk[:, 0, :, :3] = root[:, None, :] + (j * rest)[None, :, None] * d[:, None, :]
+            blk[:, 0, :, 3] = 1.0
+            blk[:, 1, :, :] = np.array([0.0, 0.0, -1.0, 0.0], np.float32)
+            blk[:, 2, :, :] = 0.0
+    finally:
+        np.seterr(**old)
+    return out
+
+
+def shard_range(num_strands, rank, nranks):
+    """Contiguous strand range [lo, hi) owned by `rank`."""
+    lo = (num_strands * rank) // nranks
+    hi = (num_strands * (rank + 1)) // nranks
+    return lo, hi
