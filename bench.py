@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--workload", default="ns_full", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spt", type=int, default=0, help="strands per thread (0 auto)")
+    ap.add_argument("--flags", default=None, help="override the workload's feature flags, e.g. grid+windB (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -213,6 +214,9 @@ def main():
         nccl_id = bytes(idt.cpu().tolist())
 
     S, N, L, flags_s, desc = WORKLOADS[args.workload]
+    if args.flags is not None:
+        flags_s = args.flags
+        desc += " [flags overridden: %s]" % flags_s
     flags = parse_flags(rvh, flags_s)
     grid_on = bool(flags & rvh.GRID_ON)
     rest = float(np.float32(L) / np.float32(N - 1))

@@ -120,15 +120,16 @@ int rvh_download_grid(rvh_ctx* ctx, void* cells, size_t bytes);
 int rvh_draw_indirect(rvh_ctx* ctx, uint32_t out[4]);   /* {S,1,0,0}, compute.comp:126-130,302 */
 
 /* Debug/test hooks: run the step split at the shader's barriers.  phase bits:
- * 1 = integrate+FTL (+corrected velocity, + splat when the grid is on), 2 = gather. */
+ * 1 = integrate+FTL+corrected velocity (+ splat and all-reduce when the grid is on),
+ * 2 = grid finalize + gather. */
 int rvh_step_phases(rvh_ctx* ctx, float dt, float total_time, int phases);
 
 /* Per-kernel CUDA-event timing (for the roofline figure).  When enabled every step
  * brackets its kernels with events; rvh_profile_read returns accumulated milliseconds
  * and launch counts since the last call: [0] ftl_step, [1] grid_gather, [2] grid
- * all-reduce, [3] grid clear. */
+ * all-reduce, [3] grid clear, [4] grid_splat, [5] grid_finalize. */
 int rvh_profile_enable(rvh_ctx* ctx, int on);
-int rvh_profile_read(rvh_ctx* ctx, float ms[4], int launches[4]);
+int rvh_profile_read(rvh_ctx* ctx, float ms[6], int launches[6]);
 
 int rvh_sync(rvh_ctx* ctx);
 float rvh_last_step_ms(rvh_ctx* ctx);

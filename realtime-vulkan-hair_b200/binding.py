@@ -210,10 +210,10 @@ class HairSim:
         self._check(self.L.rvh_profile_enable(self.ctx, int(on)), "rvh_profile_enable")
 
     def profile_read(self):
-        ms = (C.c_float * 4)()
-        n = (C.c_int * 4)()
+        ms = (C.c_float * 6)()
+        n = (C.c_int * 6)()
         self._check(self.L.rvh_profile_read(self.ctx, ms, n), "rvh_profile_read")
-        names = ["ftl_step", "grid_gather", "grid_allreduce", "grid_clear"]
+        names = ["ftl_step", "grid_gather", "grid_allreduce", "grid_clear", "grid_splat", "grid_finalize"]
         return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(names)}
 
     def sync(self):

@@ -47,7 +47,7 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int kNcclInt64 = 4, kNcclSum = 0;
 
-enum { EV_K1 = 0, EV_K2, EV_AR, EV_CLEAR, EV_COUNT };
+enum { EV_K1 = 0, EV_K2, EV_AR, EV_CLEAR, EV_SPLAT, EV_FINALIZE, EV_COUNT };
 
 }  // namespace
 
@@ -57,7 +57,10 @@ struct rvh_ctx {
     cudaStream_t stream = nullptr;
     float* planes = nullptr;              // [6][N][S_pad]
     float* corr = nullptr;                // [3][N][S_pad] (RVH_KEEP_CORRECTION)
-    unsigned long long* grid = nullptr;   // [G^3][4] int64
+    unsigned long long* grid = nullptr;   // [G^3][4] int64 accumulators
+    float4* fgrid = nullptr;              // [G^3] float cells for the gather (k_grid_finalize)
+    float* bbox = nullptr;                // [blocks][6] per-block bounding boxes (k_ftl_step -> k_grid_splat)
+    int k1_blocks = 0;
     size_t grid_bytes = 0;
     int* perm = nullptr;                  // internal -> external strand index (Morton order)
     void* aos_dev = nullptr;              // Strand[S] staging / interop target
@@ -77,8 +80,8 @@ struct rvh_ctx {
     bool profiling = false;
     std::vector<cudaEvent_t> pev;         // pairs, recycled
     std::vector<int> pev_kind; size_t pev_used = 0;
-    float prof_ms[EV_COUNT] = { 0, 0, 0, 0 };
-    int prof_n[EV_COUNT] = { 0, 0, 0, 0 };
+    float prof_ms[EV_COUNT] = { 0, 0, 0, 0, 0, 0 };
+    int prof_n[EV_COUNT] = { 0, 0, 0, 0, 0, 0 };
     long long launches = 0;
     std::string err;
 };
@@ -119,17 +122,21 @@ void prof_collect(rvh_ctx* c) {   // caller has synchronised the stream
     c->pev_used = 0;
 }
 
-template <int V, bool GRID, bool WIND>
+template <int V, bool WIND, int NELL, bool BBOX>
 void launch_k1(rvh_ctx* c) {
-    const int threads = (c->S_pad + V - 1) / V;
-    const int blocks = (threads + kBlock - 1) / kBlock;
-    k_ftl_step<V, GRID, WIND><<<blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->grid);
+    k_ftl_step<V, WIND, NELL, BBOX><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->bbox);
+}
+template <int V, bool WIND, int NELL>
+void launch_k1_b(rvh_ctx* c, bool bbox) {
+    if (bbox) launch_k1<V, WIND, NELL, true>(c); else launch_k1<V, WIND, NELL, false>(c);
 }
 template <int V>
-void launch_k1_v(rvh_ctx* c, bool grid, bool wind) {
-    if (grid) { if (wind) launch_k1<V, true, true>(c); else launch_k1<V, true, false>(c); }
-    else      { if (wind) launch_k1<V, false, true>(c); else launch_k1<V, false, false>(c); }
+void launch_k1_v(rvh_ctx* c, bool bbox, bool wind) {
+    const bool five = c->P.n_ell == 5;     // the reference scene's collider count gets the unrolled kernel
+    if (wind) { if (five) launch_k1_b<V, true, 5>(c, bbox); else launch_k1_b<V, true, -1>(c, bbox); }
+    else      { if (five) launch_k1_b<V, false, 5>(c, bbox); else launch_k1_b<V, false, -1>(c, bbox); }
 }
+size_t splat_smem(const rvh_ctx* c) { return (size_t)4 * kBoxCells * sizeof(int) + (size_t)6 * (c->N - 1) * 33 * sizeof(float); }
 
 int do_step(rvh_ctx* ctx, float dt, float total_time, int phases) {
     if (!ctx->uploaded) return fail(ctx, RVH_ERR_STATE, "rvh_step before rvh_upload_strands_aos");
@@ -160,6 +167,13 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases) {
         prof_end(ctx);
         ctx->launches += 1;
         CU(cudaGetLastError());
+        if (grid) {
+            prof_begin(ctx, EV_SPLAT);
+            k_grid_splat<<<ctx->k1_blocks, kSplatThreads, splat_smem(ctx), ctx->stream>>>(ctx->P, ctx->planes, ctx->bbox, ctx->grid, kBlock * ctx->V);
+            prof_end(ctx);
+            ctx->launches += 1;
+            CU(cudaGetLastError());
+        }
         if (grid && ctx->nranks > 1) {
             prof_begin(ctx, EV_AR);
             int r = g_nccl.AllReduce(ctx->grid, ctx->grid, ctx->grid_bytes / 8, kNcclInt64, kNcclSum, ctx->comm, ctx->stream);
@@ -168,12 +182,16 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases) {
         }
     }
     if ((phases & 2) && grid) {
+        const int cells = ctx->P.G * ctx->P.G * ctx->P.G;
+        prof_begin(ctx, EV_FINALIZE);
+        k_grid_finalize<<<(cells + 255) / 256, 256, 0, ctx->stream>>>((const long long*)ctx->grid, ctx->fgrid, cells, ctx->P.int32_wrap);
+        prof_end(ctx);
         prof_begin(ctx, EV_K2);
         const size_t total = (size_t)(ctx->N - 1) * ctx->S_pad;
         const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 64);
-        k_grid_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->P, ctx->planes, (const long long*)ctx->grid);
+        k_grid_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->fgrid);
         prof_end(ctx);
-        ctx->launches += 1;
+        ctx->launches += 2;
         CU(cudaGetLastError());
     }
     if (ctx->interop_aos) {
@@ -206,7 +224,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->S_pad = ((c->S + 127) / 128) * 128;
     c->rank = rank; c->nranks = nranks;
     int V = cfg->strands_per_thread;
-    if (V != 1 && V != 2 && V != 4) V = c->S >= 262144 ? 4 : (c->S >= 65536 ? 2 : 1);
+    if (V != 1 && V != 2 && V != 4) V = c->S >= 65536 ? 2 : 1;     // measured on B200: 2 strands per thread is fastest at scale
     c->V = V;
     ctx = c;
 #define CUC(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e2_); rvh_destroy(c); return fail(nullptr, RVH_ERR_CUDA, m_); } } while (0)
@@ -222,6 +240,11 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->grid_bytes = G * G * G * 4 * sizeof(long long);
     CUC(cudaMalloc(&c->grid, c->grid_bytes));
     CUC(cudaMemsetAsync(c->grid, 0, c->grid_bytes, c->stream));
+    CUC(cudaMalloc(&c->fgrid, G * G * G * sizeof(float4)));
+    CUC(cudaMemsetAsync(c->fgrid, 0, G * G * G * sizeof(float4), c->stream));
+    c->k1_blocks = ((c->S_pad + V - 1) / V + kBlock - 1) / kBlock;
+    CUC(cudaMalloc(&c->bbox, sizeof(float) * 6 * c->k1_blocks));
+    CUC(cudaFuncSetAttribute(k_grid_splat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)splat_smem(c)));
     c->aos_bytes = (size_t)c->S * 48 * c->N;
     CUC(cudaMalloc(&c->aos_dev, c->aos_bytes));
     CUC(cudaEventCreate(&c->ev_a)); CUC(cudaEventCreate(&c->ev_b));
@@ -454,7 +477,7 @@ int rvh_profile_enable(rvh_ctx* ctx, int on) {
     return RVH_OK;
 }
 
-int rvh_profile_read(rvh_ctx* ctx, float ms[4], int launches[4]) {
+int rvh_profile_read(rvh_ctx* ctx, float ms[6], int launches[6]) {
     if (!ctx) return RVH_ERR_INVALID;
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -485,7 +508,7 @@ void rvh_destroy(rvh_ctx* c) {
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->interop_aos) cudaFree(c->interop_aos);
     if (c->interop_mem) cudaDestroyExternalMemory(c->interop_mem);
-    cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->perm); cudaFree(c->aos_dev);
+    cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->fgrid); cudaFree(c->bbox); cudaFree(c->perm); cudaFree(c->aos_dev);
     cudaFree(c->sort_tmp); cudaFree(c->sort_keys); cudaFree(c->sort_keys_out); cudaFree(c->sort_ids);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
     if (c->ev_a) cudaEventDestroy(c->ev_a);

@@ -52,8 +52,13 @@ def check_state(gpu, ref, rest, N, vel_dt=DT, what=""):
     assert verr <= POS_TOL_REL * L / float(vel_dt), "%s velocity error %.3e" % (what, verr)
     seg = np.linalg.norm(gpu[:, 0, 1:, :3].astype(np.float64) - gpu[:, 0, :-1, :3], axis=2)
     seg_ref = np.linalg.norm(ref[:, 0, 1:, :3].astype(np.float64) - ref[:, 0, :-1, :3], axis=2)
-    assert np.abs(seg / rest - 1).max() <= SEG_TOL_REL, "%s segment drift %.3e" % (what, np.abs(seg / rest - 1).max())
-    assert np.abs(seg - seg_ref).max() / rest <= SEG_TOL_REL
+    # float32 coordinates of magnitude |p| cannot resolve a length to better than a few ulp(|p|):
+    # the 1e-5 relative bar is applied above that representability floor (it only binds for
+    # N=64, where rest = 0.04 and 1e-5*rest = 4e-7 is about one ulp of a coordinate near 4).
+    floor = 4.0 * float(np.spacing(np.float32(np.abs(ref[:, 0, :, :3]).max())))
+    seg_tol = max(SEG_TOL_REL * rest, floor)
+    assert np.abs(seg - rest).max() <= seg_tol, "%s segment drift %.3e" % (what, np.abs(seg / rest - 1).max())
+    assert np.abs(seg - seg_ref).max() <= seg_tol, "%s segment mismatch vs oracle %.3e" % (what, np.abs(seg - seg_ref).max())
     assert np.array_equal(bits(gpu[:, 0, 0]), bits(ref[:, 0, 0])), "roots must be bit-unchanged"
     assert np.all(gpu[:, 0, :, 3] == 1.0) and np.all(gpu[:, 1, :, 3] == 0.0)
     return perr, verr
