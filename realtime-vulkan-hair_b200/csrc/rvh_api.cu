@@ -59,7 +59,6 @@ struct rvh_ctx {
     float* corr = nullptr;                // [3][N][S_pad] (RVH_KEEP_CORRECTION)
     unsigned long long* grid = nullptr;   // [G^3][4] int64 accumulators
     float4* fgrid = nullptr;              // [G^3] float cells for the gather (k_grid_finalize)
-    float* bbox = nullptr;                // [blocks][6] per-block bounding boxes (k_ftl_step -> k_grid_splat)
     int k1_blocks = 0;
     size_t grid_bytes = 0;
     int* perm = nullptr;                  // internal -> external strand index (Morton order)
@@ -122,21 +121,16 @@ void prof_collect(rvh_ctx* c) {   // caller has synchronised the stream
     c->pev_used = 0;
 }
 
-template <int V, bool WIND, int NELL, bool BBOX>
-void launch_k1(rvh_ctx* c) {
-    k_ftl_step<V, WIND, NELL, BBOX><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->bbox);
-}
 template <int V, bool WIND, int NELL>
-void launch_k1_b(rvh_ctx* c, bool bbox) {
-    if (bbox) launch_k1<V, WIND, NELL, true>(c); else launch_k1<V, WIND, NELL, false>(c);
+void launch_k1(rvh_ctx* c) {
+    k_ftl_step<V, WIND, NELL><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr);
 }
 template <int V>
-void launch_k1_v(rvh_ctx* c, bool bbox, bool wind) {
+void launch_k1_v(rvh_ctx* c, bool wind) {
     const bool five = c->P.n_ell == 5;     // the reference scene's collider count gets the unrolled kernel
-    if (wind) { if (five) launch_k1_b<V, true, 5>(c, bbox); else launch_k1_b<V, true, -1>(c, bbox); }
-    else      { if (five) launch_k1_b<V, false, 5>(c, bbox); else launch_k1_b<V, false, -1>(c, bbox); }
+    if (wind) { if (five) launch_k1<V, true, 5>(c); else launch_k1<V, true, -1>(c); }
+    else      { if (five) launch_k1<V, false, 5>(c); else launch_k1<V, false, -1>(c); }
 }
-size_t splat_smem(const rvh_ctx* c) { return (size_t)4 * kBoxCells * sizeof(int) + (size_t)6 * (c->N - 1) * 33 * sizeof(float); }
 
 int do_step(rvh_ctx* ctx, float dt, float total_time, int phases) {
     if (!ctx->uploaded) return fail(ctx, RVH_ERR_STATE, "rvh_step before rvh_upload_strands_aos");
@@ -149,7 +143,7 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases) {
     P.wind_mode = (flags & RVH_WIND_B) ? 2 : ((flags & RVH_WIND_A) ? 1 : 0);
     if (wind) {
         P.wind_s2T = 2.0f * std::sin(total_time * 2.0f);
-        P.wind_T3 = total_time * 3.0f;
+        P.wind_T3 = (float)std::fmod((double)(total_time * 3.0f), 6.283185307179586);   // sin(5z + 3T): keep the argument bounded
         P.wind_amp = (P.wind_mode == 2) ? 7.0f * wind_fbm(total_time) : 10.0f;
     }
     if (phases & 1) {
@@ -160,16 +154,16 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases) {
         }
         prof_begin(ctx, EV_K1);
         switch (ctx->V) {
-            case 4: launch_k1_v<4>(ctx, grid, wind); break;
-            case 2: launch_k1_v<2>(ctx, grid, wind); break;
-            default: launch_k1_v<1>(ctx, grid, wind); break;
+            case 4: launch_k1_v<4>(ctx, wind); break;
+            case 2: launch_k1_v<2>(ctx, wind); break;
+            default: launch_k1_v<1>(ctx, wind); break;
         }
         prof_end(ctx);
         ctx->launches += 1;
         CU(cudaGetLastError());
         if (grid) {
             prof_begin(ctx, EV_SPLAT);
-            k_grid_splat<<<ctx->k1_blocks, kSplatThreads, splat_smem(ctx), ctx->stream>>>(ctx->P, ctx->planes, ctx->bbox, ctx->grid, kBlock * ctx->V);
+            k_grid_splat<<<ctx->S_pad / kSplatThreads, kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid);
             prof_end(ctx);
             ctx->launches += 1;
             CU(cudaGetLastError());
@@ -243,8 +237,6 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     CUC(cudaMalloc(&c->fgrid, G * G * G * sizeof(float4)));
     CUC(cudaMemsetAsync(c->fgrid, 0, G * G * G * sizeof(float4), c->stream));
     c->k1_blocks = ((c->S_pad + V - 1) / V + kBlock - 1) / kBlock;
-    CUC(cudaMalloc(&c->bbox, sizeof(float) * 6 * c->k1_blocks));
-    CUC(cudaFuncSetAttribute(k_grid_splat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)splat_smem(c)));
     c->aos_bytes = (size_t)c->S * 48 * c->N;
     CUC(cudaMalloc(&c->aos_dev, c->aos_bytes));
     CUC(cudaEventCreate(&c->ev_a)); CUC(cudaEventCreate(&c->ev_b));
@@ -508,7 +500,7 @@ void rvh_destroy(rvh_ctx* c) {
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->interop_aos) cudaFree(c->interop_aos);
     if (c->interop_mem) cudaDestroyExternalMemory(c->interop_mem);
-    cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->fgrid); cudaFree(c->bbox); cudaFree(c->perm); cudaFree(c->aos_dev);
+    cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->fgrid); cudaFree(c->perm); cudaFree(c->aos_dev);
     cudaFree(c->sort_tmp); cudaFree(c->sort_keys); cudaFree(c->sort_keys_out); cudaFree(c->sort_ids);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
     if (c->ev_a) cudaEventDestroy(c->ev_a);

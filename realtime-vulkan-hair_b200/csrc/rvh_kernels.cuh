@@ -70,44 +70,20 @@ __device__ __forceinline__ AxisCells axis_cells(float p, float origin, float h, 
     return a;
 }
 
-// ---- direct (slow-path) splat of one corner into the global int64 grid ------------------------
-__device__ __forceinline__ void global_add4(unsigned long long* __restrict__ grid, int idx, int c0, int c1, int c2, int c3) {
-    unsigned long long* cell = grid + 4 * (size_t)idx;
-    if (c0) atomicAdd(cell + 0, (unsigned long long)(long long)c0);
-    if (c1) atomicAdd(cell + 1, (unsigned long long)(long long)c1);
-    if (c2) atomicAdd(cell + 2, (unsigned long long)(long long)c2);
-    if (c3) atomicAdd(cell + 3, (unsigned long long)(long long)c3);
+// ---- P2 splat: compute.comp:231-252 -----------------------------------------------------------
+// Per corner the shader adds int(SCALE * (w * v_k)) and int(SCALE * w), truncated toward zero; the float
+// operations below are ordered exactly as the shader orders them, so the integers are the reference's.
+// The accumulators are int64 (int32 overflows beyond ~50K strands); integer sums are
+// order-independent, which is what makes the warp aggregation below (and the multi-GPU all-reduce) exact.
+__device__ __forceinline__ void global_add(unsigned long long* __restrict__ p, long long v) {
+    if (v) atomicAdd(p, (unsigned long long)v);                        // RED.E.ADD.64, fire and forget
 }
 
-// ---- P2 splat of one point: compute.comp:231-252 ------------------------------------------
-// Per corner: int(SCALE * (w * v_k)) and int(SCALE * w), truncated toward zero, exactly as the
-// shader orders the float operations.  With a CTA-private box (BOX=true) the 32-bit partial sums
-// go to shared memory (see k_grid_splat); otherwise straight to the global int64 grid.
-struct SplatBox {
-    int* bx; int* by; int* bz; int* bd;     // component-major int32 accumulators in shared memory
-    int lo[3], n[3];                        // first cell and extent (cells) covered by the box
-    int sy, sz;                             // odd strides (bank spreading)
-    int* sat;                               // set when a cell hit its capacity
-};
-// A box cell may hold at most kDensLimit of density: every admitted velocity contribution obeys
-// |c_k| <= kVBound * (c_d + 1), so |sum c_k| <= kVBound * (kDensLimit + 65536) < 2^31.
-constexpr float kVBound = 15.9f;
-constexpr int kDensLimit = (int)(2147483647.0 / 16.0) - 65536;
-
-template <bool BOX>
-__device__ __forceinline__ void splat_point(const StepParams& P, unsigned long long* __restrict__ grid, const SplatBox* B,
-                                            float px, float py, float pz, float vx, float vy, float vz) {
-    const AxisCells X = axis_cells(px, P.origin[0], P.h, P.G);
-    const AxisCells Y = axis_cells(py, P.origin[1], P.h, P.G);
-    const AxisCells Z = axis_cells(pz, P.origin[2], P.h, P.G);
-    bool fast = false;
-    int bbase = 0;
-    if (BOX) {
-        const int rx = X.f - B->lo[0], ry = Y.f - B->lo[1], rz = Z.f - B->lo[2];
-        const float vinf = fmaxf(fabsf(vx), fmaxf(fabsf(vy), fabsf(vz)));
-        fast = (rx >= 0) & (ry >= 0) & (rz >= 0) & (rx <= B->n[0] - 2) & (ry <= B->n[1] - 2) & (rz <= B->n[2] - 2) & (vinf <= kVBound);
-        bbase = rx + ry * B->sy + rz * B->sz;
-    }
+// Slow path: one lane splats its point straight into the global grid (8 corners x 4 atomics).
+// 64-bit conversions, so |SCALE*w*v| >= 2^31 keeps its value as in the int64 oracle.
+__device__ __forceinline__ void splat_point_direct(const StepParams& P, unsigned long long* __restrict__ grid,
+                                                   const AxisCells& X, const AxisCells& Y, const AxisCells& Z,
+                                                   float vx, float vy, float vz) {
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
         if (!(a ? X.ok1 : X.ok0)) continue;
@@ -120,29 +96,87 @@ __device__ __forceinline__ void splat_point(const StepParams& P, unsigned long l
             for (int c = 0; c < 2; ++c) {
                 if (!(c ? Z.ok1 : Z.ok0)) continue;
                 const float tw = __fmul_rn(xyw, c ? Z.w1 : Z.w0);
-                // int(SCALE * weightedVelocity.k), int(SCALE * totalWeight): truncation toward zero
-                const int c0 = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vx)));
-                const int c1 = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vy)));
-                const int c2 = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vz)));
-                const int c3 = __float2int_rz(__fmul_rn(P.scale, tw));
-                const int idx = (X.f + a) + (Y.f + b) * P.G + (Z.f + c) * P.G * P.G;
-                if (BOX && fast) {
-                    const int cell = bbase + a + b * B->sy + c * B->sz;
-                    const int old = atomicAdd(B->bd + cell, c3);
-                    if (old + c3 <= kDensLimit) {
-                        if (c0) atomicAdd(B->bx + cell, c0);
-                        if (c1) atomicAdd(B->by + cell, c1);
-                        if (c2) atomicAdd(B->bz + cell, c2);
-                    } else {                       // cell full: take the density back, go to the global grid
-                        atomicAdd(B->bd + cell, -c3);
-                        *B->sat = 1;
-                        global_add4(grid, idx, c0, c1, c2, c3);
-                    }
-                } else {
-                    global_add4(grid, idx, c0, c1, c2, c3);
-                }
+                unsigned long long* cell = grid + 4 * (size_t)((X.f + a) + (Y.f + b) * P.G + (Z.f + c) * P.G * P.G);
+                global_add(cell + 0, __float2ll_rz(__fmul_rn(P.scale, __fmul_rn(tw, vx))));
+                global_add(cell + 1, __float2ll_rz(__fmul_rn(P.scale, __fmul_rn(tw, vy))));
+                global_add(cell + 2, __float2ll_rz(__fmul_rn(P.scale, __fmul_rn(tw, vz))));
+                global_add(cell + 3, __float2ll_rz(__fmul_rn(P.scale, tw)));
             }
         }
+    }
+}
+
+// Warp-aggregated splat of one ROW: lane = strand, all 32 lanes hold the same point index of 32
+// neighbouring strands.  Strands are Morton-ordered by root, so the 32 points of a row share their base
+// cell (or split over very few cells).  For every group of lanes with the same base cell the 32
+// per-lane integers (8 corners x {vx,vy,vz,density}) are summed across the warp with REDUX.SUM -- exact,
+// they are integers -- and ONE warp-wide RED.64 with 32 distinct addresses (8 cells x 32 bytes) carries the
+// group's total to the grid: 32x fewer atomics than the shader's one-atomic-per-point-per-corner scheme,
+// no shared-memory staging, no bounding boxes.
+constexpr int kSplatMaxGroups = 6;        // more distinct cells than this in one row: lanes go direct
+constexpr float kSplatAggVmax = 60.0f;    // |c| <= 6e7 per lane, so a 32-lane int32 sum cannot overflow
+
+__device__ __forceinline__ int pick_by_lane(const int (&s)[32], int lane) {
+    int t16[16], t8[8], t4[4], t2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t16[i] = b4 ? s[i + 16] : s[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t8[i] = b3 ? t16[i + 8] : t16[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t4[i] = b2 ? t8[i + 4] : t8[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) t2[i] = b1 ? t4[i + 2] : t4[i];
+    return b0 ? t2[1] : t2[0];
+}
+
+__device__ __forceinline__ void splat_row(const StepParams& P, unsigned long long* __restrict__ grid, int lane, bool live,
+                                          float px, float py, float pz, float vx, float vy, float vz) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const AxisCells X = axis_cells(px, P.origin[0], P.h, P.G);
+    const AxisCells Y = axis_cells(py, P.origin[1], P.h, P.G);
+    const AxisCells Z = axis_cells(pz, P.origin[2], P.h, P.G);
+    const bool touches = live && (X.ok0 || X.ok1) && (Y.ok0 || Y.ok1) && (Z.ok0 || Z.ok1);
+    const float vinf = fmaxf(fabsf(vx), fmaxf(fabsf(vy), fabsf(vz)));
+    const bool fast = vinf <= kSplatAggVmax;                           // false for NaN too
+    // base-cell key; f is clamped to [-2, G] by axis_cells, so (f + 2) < G + 3
+    const int W = P.G + 3;
+    const int key = touches ? (X.f + 2) + ((Y.f + 2) + (Z.f + 2) * W) * W : -1;
+    const unsigned same = __match_any_sync(kFull, key);
+    const bool leader = touches && (lane == __ffs(same) - 1);
+    unsigned leaders = __ballot_sync(kFull, leader);
+    if (leaders == 0u) return;                                         // the whole row is outside the grid
+    if (__popc(leaders) > kSplatMaxGroups || __any_sync(kFull, touches && !fast)) {
+        if (touches) splat_point_direct(P, grid, X, Y, Z, vx, vy, vz);
+        return;
+    }
+    // the 32 integers of this lane's point, index j = corner * 4 + component, corner = a + 2b + 4c
+    int c[32];
+#pragma unroll
+    for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const float tw = __fmul_rn(__fmul_rn(a ? X.w1 : X.w0, b ? Y.w1 : Y.w0), cz ? Z.w1 : Z.w0);
+                const int j = 4 * (a + 2 * b + 4 * cz);
+                c[j + 0] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vx)));
+                c[j + 1] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vy)));
+                c[j + 2] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vz)));
+                c[j + 3] = __float2int_rz(__fmul_rn(P.scale, tw));
+            }
+    const int comp = lane & 3, ca = (lane >> 2) & 1, cb = (lane >> 3) & 1, cc = (lane >> 4) & 1;
+    while (leaders) {
+        const int L = __ffs(leaders) - 1;
+        leaders &= leaders - 1;
+        const int member = -(int)((same >> L) & 1u);                   // all-ones for the lanes of leader L's group
+        int s[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[j] = __reduce_add_sync(kFull, c[j] & member);
+        const int mine = pick_by_lane(s, lane);
+        const int fx = __shfl_sync(kFull, X.f, L) + ca, fy = __shfl_sync(kFull, Y.f, L) + cb, fz = __shfl_sync(kFull, Z.f, L) + cc;
+        const bool ok = (unsigned)fx < (unsigned)P.G && (unsigned)fy < (unsigned)P.G && (unsigned)fz < (unsigned)P.G;
+        if (ok) global_add(grid + 4 * (size_t)(fx + (fy + fz * P.G) * P.G) + comp, (long long)mine);
     }
 }
 
@@ -186,39 +220,20 @@ __device__ __forceinline__ void gather_point(const StepParams& P, const float4* 
 }
 
 // ---- wind trigonometry ---------------------------------------------------------------------------
-// sin/cos with a two-constant Cody-Waite reduction by pi and degree-9/10 polynomials on
-// [-pi/2, pi/2]: absolute error < 2e-7 for |x| < 1e4, which is far inside what the wind force
-// needs (it enters positions multiplied by dt^2).  No slow path, no local memory, ~14 instructions.
-__device__ __forceinline__ float reduce_pi(float x, unsigned& sign) {
-    const float kf = fmaf(x, 0.31830987f, 12582912.0f);     // round(x/pi) in the low mantissa bits
-    sign = __float_as_uint(kf) << 31;                          // parity of k
-    const float k = kf - 12582912.0f;
-    float r = fmaf(k, -3.141592741f, x);
-    r = fmaf(k, 8.742277657e-08f, r);
-    return r;
-}
-__device__ __forceinline__ float sin_bounded(float x) {
-    unsigned sign;
-    const float r = reduce_pi(x, sign), r2 = r * r;
-    float p = fmaf(r2, 2.5992781e-06f, -0.00019806201f);
-    p = fmaf(r2, p, 0.0083330106f);
-    p = fmaf(r2, p, -0.16666657f);
-    const float s = fmaf(r * r2, p, r);
-    return fminf(fmaxf(__uint_as_float(__float_as_uint(s) ^ sign), -1.0f), 1.0f);
-}
-__device__ __forceinline__ float cos_bounded(float x) {
-    unsigned sign;
-    const float r = reduce_pi(x, sign), r2 = r * r;
-    float p = fmaf(r2, -2.6073479e-07f, 2.4761655e-05f);
-    p = fmaf(r2, p, -0.0013888398f);
-    p = fmaf(r2, p, 0.041666642f);
-    p = fmaf(r2, p, -0.5f);
-    const float c = fmaf(r2, p, 1.0f);
-    return fminf(fmaxf(__uint_as_float(__float_as_uint(c) ^ sign), -1.0f), 1.0f);
-}
+// The wind force enters positions multiplied by dt^2 (2.8e-4 at 60 Hz), so MUFU.SIN/COS accuracy is far
+// more than the 1e-4*L position tolerance needs: for the bounded arguments used here (|x| < ~200; the host
+// reduces the time term mod 2*pi) the absolute error is < 2e-5, i.e. < 1e-8 in position.  2 instructions
+// each instead of a 14-instruction Cody-Waite + polynomial evaluation.
+__device__ __forceinline__ float sin_bounded(float x) { return __sinf(x); }
+__device__ __forceinline__ float cos_bounded(float x) { return __cosf(x); }
 __device__ __forceinline__ float rsqrt_fast(float x) {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
@@ -293,14 +308,15 @@ __device__ __forceinline__ PointOut point_update(const StepParams& P, float cx, 
             const float oy = fmaf(E.xf[4], ux, fmaf(E.xf[5], uy, fmaf(E.xf[6], uz, E.xf[7])));
             const float oz = fmaf(E.xf[8], ux, fmaf(E.xf[9], uy, fmaf(E.xf[10], uz, E.xf[11])));
             const float ex = cx - ox, ey = cy - oy, ez = cz - oz;
-            const float d = sqrtf(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
+            const float e2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+            const float d = e2 > 0.f ? e2 * rsqrt_fast(e2) : 0.f;
             const float nx = fmaf(E.nt[0], qx, fmaf(E.nt[1], qy, E.nt[2] * qz));
             const float ny = fmaf(E.nt[3], qx, fmaf(E.nt[4], qy, E.nt[5] * qz));
             const float nz = fmaf(E.nt[6], qx, fmaf(E.nt[7], qy, E.nt[8] * qz));
             const float s = P.penalty_k * d * rsqrt_fast(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
             ax = fmaf(s, nx, ax); ay = fmaf(s, ny, ay); az = fmaf(s, nz, az);
         }
-        const float ih = __frcp_rn((float)__popc(hit));                 // :182-184
+        const float ih = rcp_fast((float)__popc(hit));                  // :182-184
         fx = fmaf(ax, ih, fx); fy = fmaf(ay, ih, fy); fz = fmaf(az, ih, fz);
     }
 
@@ -326,16 +342,12 @@ __device__ __forceinline__ PointOut point_update(const StepParams& P, float cx, 
 // One thread owns V consecutive strands and walks them root->tip together (V independent
 // dependency chains per thread).  Point i's velocity is final only once d_{i+1} is known
 // (compute.comp:213-215), so the velocity store trails the position by one point.
-// With BBOX the block also reduces the bounding box of its strands' new positions, which sizes
-// the shared-memory box of the splat kernel that handles the same strands.
-template <int V, bool WIND, int NELL, bool BBOX>
+template <int V, bool WIND, int NELL>
 __global__ void __launch_bounds__(kBlock)
-k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr,
-           float* __restrict__ bbox) {
+k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int s0 = t * V;
     const bool active = s0 < P.S_pad;
-    float bmin[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, bmax[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
     if (active) {
         const size_t plane = (size_t)P.N * P.S_pad;
         float* const ppx = planes + s0;
@@ -376,10 +388,6 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
                 // finalise point i-1: v_{i-1} -= d_i / dt   (compute.comp:213-215)
                 fvx[u] = fmaf(-o.dx, P.inv_dt, lvx[u]); fvy[u] = fmaf(-o.dy, P.inv_dt, lvy[u]); fvz[u] = fmaf(-o.dz, P.inv_dt, lvz[u]);
                 lvx[u] = o.vx; lvy[u] = o.vy; lvz[u] = o.vz;
-                if (BBOX && s0 + u < P.S) {
-                    bmin[0] = fminf(bmin[0], o.px); bmin[1] = fminf(bmin[1], o.py); bmin[2] = fminf(bmin[2], o.pz);
-                    bmax[0] = fmaxf(bmax[0], o.px); bmax[1] = fmaxf(bmax[1], o.py); bmax[2] = fmaxf(bmax[2], o.pz);
-                }
             }
             store_vec<V>(ppx + oi, opx); store_vec<V>(ppy + oi, opy); store_vec<V>(ppz + oi, opz);
             if (P.keep_corr) {
@@ -397,131 +405,37 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
         const size_t ol = (size_t)(P.N - 1) * P.S_pad;
         store_vec<V>(pvx + ol, lvx); store_vec<V>(pvy + ol, lvy); store_vec<V>(pvz + ol, lvz);
     }
-    if (BBOX) {
-        __shared__ float red[6][kBlock / 32];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                bmin[k] = fminf(bmin[k], __shfl_xor_sync(0xffffffffu, bmin[k], d));
-                bmax[k] = fmaxf(bmax[k], __shfl_xor_sync(0xffffffffu, bmax[k], d));
-            }
-        }
-        const int w = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { red[k][w] = bmin[k]; red[3 + k][w] = bmax[k]; }
-        }
-        __syncthreads();
-        if (threadIdx.x < 6) {
-            float v = red[threadIdx.x][0];
-            for (int q = 1; q < kBlock / 32; ++q) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][q]) : fmaxf(v, red[threadIdx.x][q]);
-            bbox[6 * blockIdx.x + threadIdx.x] = v;
-        }
-    }
 }
 
-// ---- K_splat: corrected velocities -> voxel grid ------------------------------------------------
-// Block b owns the same kBlock*V strands as block b of k_ftl_step.  Points of one ROW of neighbouring
-// strands fall into the same one or two cells (hair is dense), so a lane-per-strand splat would
-// serialise every shared-memory atomic ~13-fold.  Instead a tile of 32 strands x all rows is staged
-// through shared memory (coalesced 128-byte row segments in, transposed out) and each warp walks ONE
-// strand with lane = row: the 32 lanes then hit ~23 different cells and the atomics run conflict-light.
-// Partial sums live in a CTA-private int32 box sized from the block's bounding box (written by
-// k_ftl_step) and are flushed once with 64-bit global reductions.
-constexpr int kSplatThreads = 256;
-constexpr int kBoxCells = 3072;             // 48 KB of int32 x 4 components
-constexpr int kTileRowsMax = 63;            // N <= 64
-
-__device__ __forceinline__ void box_flush(const StepParams& P, const SplatBox& B, unsigned long long* __restrict__ grid, int ncell_padded) {
-    for (int k = threadIdx.x; k < ncell_padded; k += blockDim.x) {
-        const int d = B.bd[k], x = B.bx[k], y = B.by[k], z = B.bz[k];
-        if ((d | x | y | z) != 0) {
-            const int cz = k / B.sz, rem = k - cz * B.sz;
-            const int cy = rem / B.sy, cx = rem - cy * B.sy;
-            const int idx = (B.lo[0] + cx) + (B.lo[1] + cy) * P.G + (B.lo[2] + cz) * P.G * P.G;
-            global_add4(grid, idx, x, y, z, d);
-            B.bd[k] = 0; B.bx[k] = 0; B.by[k] = 0; B.bz[k] = 0;
-        }
-    }
-}
+// ---- K_splat: corrected velocities -> voxel grid (compute.comp:231-252) ----------------------------
+// One warp owns 32 consecutive strands and walks their rows root->tip: every load is a fully coalesced
+// 128-byte row segment of a plane, the next row is in flight while the current one is aggregated
+// (splat_row above).  Grid sized to the strand count; no shared memory.
+constexpr int kSplatThreads = 128;
 
 __global__ void __launch_bounds__(kSplatThreads)
-k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ planes, const float* __restrict__ bbox,
-             unsigned long long* __restrict__ grid, int strands_per_block) {
-    extern __shared__ int smem[];
-    __shared__ int s_sat;
-    int* box = smem;                                        // [4][kBoxCells]
-    float* tile = reinterpret_cast<float*>(smem + 4 * kBoxCells);   // [6][rows][33]
-    const int rows = P.N - 1;
-    const int s_begin = blockIdx.x * strands_per_block;
-    if (s_begin >= P.S) return;
-    const int s_end = min(s_begin + strands_per_block, P.S);
-
-    // box geometry from the block's bounding box
-    SplatBox B;
-    B.bx = box; B.by = box + kBoxCells; B.bz = box + 2 * kBoxCells; B.bd = box + 3 * kBoxCells;
-    B.sat = &s_sat;
-    {
-        const float* bb = bbox + 6 * blockIdx.x;
-        int hi[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const AxisCells lo = axis_cells(bb[k], P.origin[k], P.h, P.G), up = axis_cells(bb[3 + k], P.origin[k], P.h, P.G);
-            B.lo[k] = max(lo.f, 0);
-            hi[k] = min(up.f + 1, P.G - 1);
-            B.n[k] = max(hi[k] - B.lo[k] + 1, 2);
-        }
-        // shrink until it fits (points outside the box take the global path)
-        int n0 = B.n[0], n1 = B.n[1], n2 = B.n[2];
-        while (true) {
-            const int sy = n0 | 1, sz = (sy * n1) | 1;
-            if ((long long)sz * n2 <= kBoxCells) { B.sy = sy; B.sz = sz; break; }
-            if (n0 >= n1 && n0 >= n2) n0 = (n0 + 1) / 2;
-            else if (n1 >= n2) n1 = (n1 + 1) / 2;
-            else n2 = (n2 + 1) / 2;
-        }
-        B.n[0] = n0; B.n[1] = n1; B.n[2] = n2;
-    }
-    const int ncell = B.sz * B.n[2];
-    for (int k = threadIdx.x; k < 4 * kBoxCells; k += blockDim.x) box[k] = 0;
-    if (threadIdx.x == 0) s_sat = 0;
-    __syncthreads();
-
+k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid) {
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * kSplatThreads + threadIdx.x;           // S_pad is a multiple of 128: always in bounds
+    const bool live = s < P.S;
+    if (!__any_sync(0xffffffffu, live)) return;
     const size_t plane = (size_t)P.N * P.S_pad;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kSplatThreads / 32;
-    const int tstride = rows * 33;
-    for (int t0 = s_begin; t0 < s_end; t0 += 32) {
-        // stage rows 1..N-1 of strands t0..t0+31: lane = strand (coalesced), warp strides rows
-        for (int r = warp; r < rows; r += nwarps) {
-            const size_t g = (size_t)(r + 1) * P.S_pad + t0 + lane;
+    const float* p0 = planes + s;
+    float n[6];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) tile[k * tstride + r * 33 + lane] = __ldg(planes + k * plane + g);
+    for (int k = 0; k < 6; ++k) n[k] = __ldg(p0 + k * plane + P.S_pad);
+    size_t o = P.S_pad;
+    for (int r = 1; r < P.N; ++r) {
+        float c[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c[k] = n[k];
+        o += P.S_pad;
+        if (r + 1 < P.N) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) n[k] = __ldg(p0 + k * plane + o);
         }
-        __syncthreads();
-        // splat: lane = row (short strands: several strands share a warp pass), warps stride strands
-        const int nst = min(32, s_end - t0);
-        int lps = 32;                                   // lanes per strand
-        while ((lps >> 1) >= rows && lps > 1) lps >>= 1;
-        const int spp = 32 / lps;                       // strands per warp pass
-        const int sub = lane / lps, rl = lane % lps;
-        for (int rb = 0; rb < rows; rb += lps) {
-            const int r = rb + rl;
-            for (int sl = warp * spp + sub; sl < nst; sl += nwarps * spp) {
-                if (r < rows) {
-                    const int o = r * 33 + sl;
-                    splat_point<true>(P, grid, &B, tile[o], tile[tstride + o], tile[2 * tstride + o],
-                                      tile[3 * tstride + o], tile[4 * tstride + o], tile[5 * tstride + o]);
-                }
-            }
-        }
-        if (__syncthreads_or(s_sat)) {           // some cell reached its int32-safe capacity: empty the box
-            box_flush(P, B, grid, ncell);
-            if (threadIdx.x == 0) s_sat = 0;
-            __syncthreads();
-        }
+        splat_row(P, grid, lane, live, c[0], c[1], c[2], c[3], c[4], c[5]);
     }
-    box_flush(P, B, grid, ncell);
 }
 
 // ---- grid finalize: int64 accumulators -> float cells for the gather ---------------------------

@@ -1,0 +1,99 @@
+"""The C++ host mirror (Hair / Scene / Renderer over the C ABI): CPU tests pin Hair::Hair against the
+reference's own constructor output; GPU tests drive the reference application loop headless."""
+import os
+
+import numpy as np
+import pytest
+
+import hostmirror
+import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DT = np.float32(1.0 / 60.0)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def obj_path(tmp_path_factory):
+    mesh = np.load(os.path.join(ROOT, "tests", "golden", "mannequin_segment_mesh.npz"))
+    p = str(tmp_path_factory.mktemp("mesh") / "mannequin_segment.obj")
+    hostmirror.write_obj(p, mesh)
+    return p
+
+
+def test_struct_sizes_match_reference():
+    L = hostmirror.lib()
+    # Strand (N=10), Collider, GridCell, StrandDrawIndirect, Time   (Strand.h, Scene.h)
+    assert [L.rvhh_sizeof(i) for i in range(5)] == [480, 192, 16, 16, 8]
+
+
+def test_hair_ctor_reproduces_reference_upload_bit_exact(golden_c1, obj_path):
+    """Own OBJ reader + ear clipping + srand(8)/rand() sampling == the reference's Hair::Hair (Strand.cpp:26-191)
+    compiled from its own sources (state0 was captured from oracle/_ref/libref_host.so)."""
+    st, ind = hostmirror.hair_init(obj_path, 900, 10)
+    assert ind == list(golden_c1["indirect0"]) == [900, 1, 0, 0]
+    assert np.array_equal(bits(st), bits(golden_c1["state0"]))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/models/mannequin_segment.obj"), reason="reference tree not present")
+def test_hair_ctor_on_the_reference_asset_itself(golden_c1):
+    st, _ = hostmirror.hair_init("/root/reference/src/models/mannequin_segment.obj", 900, 10)
+    assert np.array_equal(bits(st), bits(golden_c1["state0"]))
+
+
+def test_hair_ctor_other_sizes_follow_the_same_sequence(golden_c1, obj_path):
+    # more strands extend the same rand() stream: the first 900 follicles are unchanged
+    st, ind = hostmirror.hair_init(obj_path, 2000, 10)
+    assert ind == [2000, 1, 0, 0]
+    assert np.array_equal(bits(st[:900]), bits(golden_c1["state0"]))
+    st16, _ = hostmirror.hair_init(obj_path, 900, 16)
+    assert np.array_equal(bits(st16[:, 0, 0]), bits(golden_c1["state0"][:, 0, 0]))      # same roots
+    seg = np.float32(2.5 / 15.0)
+    d = (golden_c1["state0"][:, 0, 1, :3] - golden_c1["state0"][:, 0, 0, :3]) / np.float32(2.5 / 9.0)
+    assert np.abs((st16[:, 0, 1, :3] - st16[:, 0, 0, :3]) - seg * d).max() < 1e-5
+
+
+def test_hair_ctor_errors_are_exceptions_not_exit():
+    with pytest.raises(RuntimeError):
+        hostmirror.hair_init("/nonexistent/mesh.obj", 10, 10)
+
+
+@pytest.mark.gpu
+def test_reference_application_loop_headless(golden_c1, obj_path):
+    """main.cpp:226-251 scene + `UpdateTime -> Frame -> moveSphere` (main.cpp:281-283) through the mirror, against
+    the oracle driven the same way.  4 free-running frames (valid for <~10)."""
+    import rvh_b200 as rvh
+    frames = 4
+    moves = np.tile(np.array([[-0.05, 0.02, -0.01]], np.float32), (frames, 1))
+    out, ind, total = hostmirror.run_scene(obj_path, 900, 10, rvh.GRID_ON | rvh.GRID_INT32_WRAP, frames, float(DT), moves)
+    assert ind == [900, 1, 0, 0]
+    st = golden_c1["state0"].copy()
+    cols = golden_c1["colliders"].copy()
+    p = orc.default_params(900, 10, orc.GRID_ON | orc.GRID_INT32_WRAP)
+    t = np.float32(0)
+    for f in range(frames):
+        t = np.float32(t + DT)                        # Scene::UpdateTime accumulates before the dispatch (Scene.cpp:83-86)
+        st, _ = orc.step(p, cols, DT, t, st)
+        cols[0] = orc.collider_translate(cols[0], moves[f])
+    assert abs(total - float(t)) < 1e-6
+    assert np.array_equal(bits(out[:, 0, 0]), bits(st[:, 0, 0]))
+    assert np.abs(out[:, 0, :, :3] - st[:, 0, :, :3]).max() <= 1e-3 * 2.5
+    seg = np.linalg.norm(out[:, 0, 1:, :3].astype(np.float64) - out[:, 0, :-1, :3], axis=2)
+    assert np.abs(seg / (2.5 / 9.0) - 1).max() <= 1e-5
+
+
+@pytest.mark.gpu
+def test_mirror_single_frame_matches_c_abi_path(golden_c1, obj_path):
+    import rvh_b200 as rvh
+    out, _, _ = hostmirror.run_scene(obj_path, 900, 10, rvh.GRID_ON | rvh.GRID_INT32_WRAP, 1, float(DT))
+    cfg = rvh.default_config(900, 10, flags=rvh.GRID_ON | rvh.GRID_INT32_WRAP)
+    sim = rvh.HairSim(cfg)
+    sim.set_colliders(golden_c1["colliders"])
+    sim.upload(golden_c1["state0"])
+    sim.step(float(DT), float(DT))
+    direct = sim.download()
+    sim.close()
+    assert np.array_equal(bits(out), bits(direct))
