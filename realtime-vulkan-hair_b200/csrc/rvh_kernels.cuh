@@ -237,174 +237,257 @@ __device__ __forceinline__ float rcp_fast(float x) {
     return y;
 }
 
-// ---- P1 for one point: compute.comp:144-201 -------------------------------------------------
-struct PointOut { float px, py, pz, vx, vy, vz, dx, dy, dz; };
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2) ----------------------------------
+// sm_100 issues two fp32 FMAs per lane in ONE instruction (fma.rn.f32x2 -> SASS FFMA2) and accepts a
+// scalar register broadcast to both halves.  The step is issue-bound, not pipe-bound, so pairing the
+// two strands a thread owns halves the issue slots of all straight-line arithmetic.  The code below is
+// written once over T = float (one strand per thread) or T = float2 (two strands per pack).
+template <class T> struct VecTraits;
+template <> struct VecTraits<float>  { static constexpr int n = 1; };
+template <> struct VecTraits<float2> { static constexpr int n = 2; };
+template <class T> __device__ __forceinline__ T bc(float a);
+template <> __device__ __forceinline__ float  bc<float>(float a)  { return a; }
+template <> __device__ __forceinline__ float2 bc<float2>(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float  vfma(float a, float b, float c)    { return fmaf(a, b, c); }
+__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float  vmul(float a, float b)   { return a * b; }
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float  vadd(float a, float b)   { return a + b; }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float  vsub(float a, float b)   { return a - b; }
+__device__ __forceinline__ float2 vsub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }   // a - b, one rounding
+__device__ __forceinline__ float  el(float a, int)    { return a; }
+__device__ __forceinline__ float  el(float2 a, int i) { return i ? a.y : a.x; }
+__device__ __forceinline__ void setel(float& a, int, float v)    { a = v; }
+__device__ __forceinline__ void setel(float2& a, int i, float v) { if (i) a.y = v; else a.x = v; }
+template <class T> __device__ __forceinline__ T vdot3(T ax, T ay, T az, T bx, T by, T bz) { return vfma(ax, bx, vfma(ay, by, vmul(az, bz))); }
+
+// ---- P1 for one point (or one pack of two): compute.comp:144-201 --------------------------------
+template <class T> struct PointOut { T px, py, pz, vx, vy, vz, dx, dy, dz; };
 
 // q = inv * (p,1) of ellipsoid E and |q|^2 (compute.comp:64-67)
-__device__ __forceinline__ float ellipsoid_q(const Ellipsoid& E, float cx, float cy, float cz, float& qx, float& qy, float& qz) {
-    qx = fmaf(E.inv[0], cx, fmaf(E.inv[1], cy, fmaf(E.inv[2], cz, E.inv[3])));
-    qy = fmaf(E.inv[4], cx, fmaf(E.inv[5], cy, fmaf(E.inv[6], cz, E.inv[7])));
-    qz = fmaf(E.inv[8], cx, fmaf(E.inv[9], cy, fmaf(E.inv[10], cz, E.inv[11])));
-    return fmaf(qx, qx, fmaf(qy, qy, qz * qz));
+template <class T>
+__device__ __forceinline__ T ellipsoid_q(const Ellipsoid& E, T cx, T cy, T cz, T& qx, T& qy, T& qz) {
+    qx = vfma(bc<T>(E.inv[0]), cx, vfma(bc<T>(E.inv[1]), cy, vfma(bc<T>(E.inv[2]), cz, bc<T>(E.inv[3]))));
+    qy = vfma(bc<T>(E.inv[4]), cx, vfma(bc<T>(E.inv[5]), cy, vfma(bc<T>(E.inv[6]), cz, bc<T>(E.inv[7]))));
+    qz = vfma(bc<T>(E.inv[8]), cx, vfma(bc<T>(E.inv[9]), cy, vfma(bc<T>(E.inv[10]), cz, bc<T>(E.inv[11]))));
+    return vdot3(qx, qy, qz, qx, qy, qz);
 }
 
-// NELL >= 0: number of ellipsoids known at compile time (constants become immediate constant-bank
-// operands of the FFMAs); NELL < 0: run-time count.
-template <bool WIND, int NELL>
-__device__ __forceinline__ PointOut point_update(const StepParams& P, float cx, float cy, float cz,
-                                                 float vx, float vy, float vz,
-                                                 float parx, float pary, float parz) {
-    float fx = 0.0f, fy = P.gravity_y, fz = 0.0f;                       // :150
+// Penalty force of the colliders in `hit` on ONE point (the divergent part; compute.comp:160-184).
+__device__ __forceinline__ void collision_force(const StepParams& P, unsigned hit, float cx, float cy, float cz,
+                                                float& ox, float& oy, float& oz) {
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (hit & 1u) {                                                     // sphere, :160-169
+        const float dx = cx - P.sphere_c[0], dy = cy - P.sphere_c[1], dz = cz - P.sphere_c[2];
+        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        const float rinv = rsqrt_fast(d2);
+        const float s = P.penalty_k * (P.sphere_r - d2 * rinv) * rinv;
+        ax = s * dx; ay = s * dy; az = s * dz;
+    }
+    unsigned m = hit >> 1;
+    while (m) {                                                         // ellipsoids, :170-179
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const Ellipsoid& E = P.ell[j];
+        float qx, qy, qz;
+        const float q2 = ellipsoid_q<float>(E, cx, cy, cz, qx, qy, qz);
+        const float rq = rsqrt_fast(q2);
+        const float ux = qx * rq, uy = qy * rq, uz = qz * rq;
+        const float sx = fmaf(E.xf[0], ux, fmaf(E.xf[1], uy, fmaf(E.xf[2], uz, E.xf[3])));
+        const float sy = fmaf(E.xf[4], ux, fmaf(E.xf[5], uy, fmaf(E.xf[6], uz, E.xf[7])));
+        const float sz = fmaf(E.xf[8], ux, fmaf(E.xf[9], uy, fmaf(E.xf[10], uz, E.xf[11])));
+        const float ex = cx - sx, ey = cy - sy, ez = cz - sz;
+        const float e2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+        const float d = e2 > 0.f ? e2 * rsqrt_fast(e2) : 0.f;
+        const float nx = fmaf(E.nt[0], qx, fmaf(E.nt[1], qy, E.nt[2] * qz));
+        const float ny = fmaf(E.nt[3], qx, fmaf(E.nt[4], qy, E.nt[5] * qz));
+        const float nz = fmaf(E.nt[6], qx, fmaf(E.nt[7], qy, E.nt[8] * qz));
+        const float s = P.penalty_k * d * rsqrt_fast(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+        ax = fmaf(s, nx, ax); ay = fmaf(s, ny, ay); az = fmaf(s, nz, az);
+    }
+    const float ih = rcp_fast((float)__popc(hit));                      // :182-184
+    ox = ax * ih; oy = ay * ih; oz = az * ih;
+}
+
+// NELL >= 0: number of ellipsoids known at compile time; NELL < 0: run-time count.
+template <class T, bool WIND, int NELL>
+__device__ __forceinline__ PointOut<T> point_update(const StepParams& P, T cx, T cy, T cz, T vx, T vy, T vz,
+                                                    T parx, T pary, T parz) {
+    constexpr int n = VecTraits<T>::n;
+    T fx = bc<T>(0.0f), fy = bc<T>(P.gravity_y), fz = bc<T>(0.0f);       // :150
     if (WIND) {
-        const float wx = P.wind_s2T * cos_bounded(cy * 10.0f) * sin_bounded((cy + 5.0f) * 15.0f);
-        fx = fmaf(P.wind_amp, wx, fx);
+        const T a1 = vmul(cy, bc<T>(10.0f));
+        const T a2 = vmul(vadd(cy, bc<T>(5.0f)), bc<T>(15.0f));
+        T cs, sn;
+#pragma unroll
+        for (int i = 0; i < n; ++i) { setel(cs, i, cos_bounded(el(a1, i))); setel(sn, i, sin_bounded(el(a2, i))); }
+        fx = vfma(bc<T>(P.wind_amp * P.wind_s2T), vmul(cs, sn), fx);
         if (P.wind_mode == 1) {                                         // :151
-            fz = fmaf(P.wind_amp, -fminf(fmaxf(cy * 2.0f, 0.2f), 2.0f), fz);
+            T cl;
+#pragma unroll
+            for (int i = 0; i < n; ++i) setel(cl, i, fminf(fmaxf(el(cy, i) * 2.0f, 0.2f), 2.0f));
+            fz = vfma(bc<T>(-P.wind_amp), cl, fz);
         } else {                                                        // :152
-            fy = fmaf(P.wind_amp, 4.0f * sin_bounded(fmaf(cz, 5.0f, P.wind_T3)), fy);
-            fz = fmaf(P.wind_amp, -0.6f * (cy + 3.0f), fz);
+            const T a3 = vfma(cz, bc<T>(5.0f), bc<T>(P.wind_T3));
+            T s3;
+#pragma unroll
+            for (int i = 0; i < n; ++i) setel(s3, i, sin_bounded(el(a3, i)));
+            fy = vfma(bc<T>(4.0f * P.wind_amp), s3, fy);
+            fz = vfma(bc<T>(-0.6f * P.wind_amp), vadd(cy, bc<T>(3.0f)), fz);
         }
     }
 
     // collision tests first (one predicate per collider), bodies only for the colliders hit
-    const int nell = NELL >= 0 ? NELL : P.n_ell;
-    unsigned hit = 0;
+    unsigned hit[n];
     {
-        const float dx = cx - P.sphere_c[0], dy = cy - P.sphere_c[1], dz = cz - P.sphere_c[2];
-        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        if (d2 < P.sphere_r2) hit = P.has_sphere;                       // :162
+        const T dx = vsub(cx, bc<T>(P.sphere_c[0])), dy = vsub(cy, bc<T>(P.sphere_c[1])), dz = vsub(cz, bc<T>(P.sphere_c[2]));
+        const T d2 = vdot3(dx, dy, dz, dx, dy, dz);
+#pragma unroll
+        for (int i = 0; i < n; ++i) hit[i] = (el(d2, i) < P.sphere_r2) ? (unsigned)P.has_sphere : 0u;   // :162
     }
     if (NELL >= 0) {
 #pragma unroll
         for (int j = 0; j < (NELL >= 0 ? NELL : 0); ++j) {
-            float qx, qy, qz;
-            if (ellipsoid_q(P.ell[j], cx, cy, cz, qx, qy, qz) <= 1.0f) hit |= 2u << j;   // :66
+            T qx, qy, qz;
+            const T q2 = ellipsoid_q<T>(P.ell[j], cx, cy, cz, qx, qy, qz);
+#pragma unroll
+            for (int i = 0; i < n; ++i) if (el(q2, i) <= 1.0f) hit[i] |= 2u << j;                       // :66
         }
     } else {
-        for (int j = 0; j < nell; ++j) {
-            float qx, qy, qz;
-            if (ellipsoid_q(P.ell[j], cx, cy, cz, qx, qy, qz) <= 1.0f) hit |= 2u << j;
+        for (int j = 0; j < P.n_ell; ++j) {
+            T qx, qy, qz;
+            const T q2 = ellipsoid_q<T>(P.ell[j], cx, cy, cz, qx, qy, qz);
+#pragma unroll
+            for (int i = 0; i < n; ++i) if (el(q2, i) <= 1.0f) hit[i] |= 2u << j;
         }
     }
-    if (hit) {
-        float ax = 0.f, ay = 0.f, az = 0.f;
-        if (hit & 1u) {                                                 // :160-169
-            const float dx = cx - P.sphere_c[0], dy = cy - P.sphere_c[1], dz = cz - P.sphere_c[2];
-            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-            const float rinv = rsqrt_fast(d2);
-            const float s = P.penalty_k * (P.sphere_r - d2 * rinv) * rinv;
-            ax = s * dx; ay = s * dy; az = s * dz;
+    unsigned any_hit = 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) any_hit |= hit[i];
+    if (any_hit) {
+        T ax = bc<T>(0.f), ay = bc<T>(0.f), az = bc<T>(0.f);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            if (hit[i]) {
+                float ox, oy, oz;
+                collision_force(P, hit[i], el(cx, i), el(cy, i), el(cz, i), ox, oy, oz);
+                setel(ax, i, ox); setel(ay, i, oy); setel(az, i, oz);
+            }
         }
-        unsigned m = hit >> 1;
-        while (m) {                                                     // :170-179
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const Ellipsoid& E = P.ell[j];
-            float qx, qy, qz;
-            const float q2 = ellipsoid_q(E, cx, cy, cz, qx, qy, qz);
-            const float rq = rsqrt_fast(q2);
-            const float ux = qx * rq, uy = qy * rq, uz = qz * rq;
-            const float ox = fmaf(E.xf[0], ux, fmaf(E.xf[1], uy, fmaf(E.xf[2], uz, E.xf[3])));
-            const float oy = fmaf(E.xf[4], ux, fmaf(E.xf[5], uy, fmaf(E.xf[6], uz, E.xf[7])));
-            const float oz = fmaf(E.xf[8], ux, fmaf(E.xf[9], uy, fmaf(E.xf[10], uz, E.xf[11])));
-            const float ex = cx - ox, ey = cy - oy, ez = cz - oz;
-            const float e2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-            const float d = e2 > 0.f ? e2 * rsqrt_fast(e2) : 0.f;
-            const float nx = fmaf(E.nt[0], qx, fmaf(E.nt[1], qy, E.nt[2] * qz));
-            const float ny = fmaf(E.nt[3], qx, fmaf(E.nt[4], qy, E.nt[5] * qz));
-            const float nz = fmaf(E.nt[6], qx, fmaf(E.nt[7], qy, E.nt[8] * qz));
-            const float s = P.penalty_k * d * rsqrt_fast(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
-            ax = fmaf(s, nx, ax); ay = fmaf(s, ny, ay); az = fmaf(s, nz, az);
-        }
-        const float ih = rcp_fast((float)__popc(hit));                  // :182-184
-        fx = fmaf(ax, ih, fx); fy = fmaf(ay, ih, fy); fz = fmaf(az, ih, fz);
+        fx = vadd(fx, ax); fy = vadd(fy, ay); fz = vadd(fz, az);
     }
 
-    PointOut o;
-    const float prx = fmaf(P.dt2, fx, fmaf(P.dt, vx, cx));              // :187
-    const float pry = fmaf(P.dt2, fy, fmaf(P.dt, vy, cy));
-    const float prz = fmaf(P.dt2, fz, fmaf(P.dt, vz, cz));
-    const float ddx = prx - parx, ddy = pry - pary, ddz = prz - parz;   // :191-192
-    const float sc = P.rest * rsqrt_fast(fmaf(ddx, ddx, fmaf(ddy, ddy, ddz * ddz)));
-    o.px = fmaf(sc, ddx, parx); o.py = fmaf(sc, ddy, pary); o.pz = fmaf(sc, ddz, parz);
-    float nvx = (o.px - cx) * P.vel_scale, nvy = (o.py - cy) * P.vel_scale, nvz = (o.pz - cz) * P.vel_scale;  // :195-197
-    const float l2 = fmaf(nvx, nvx, fmaf(nvy, nvy, nvz * nvz));
-    if (l2 > P.vmax2) {                                                 // :198-200
-        const float s = P.vmax * rsqrt_fast(l2);
-        nvx *= s; nvy *= s; nvz *= s;
+    PointOut<T> o;
+    const T dt = bc<T>(P.dt), dt2 = bc<T>(P.dt2);
+    const T prx = vfma(dt2, fx, vfma(dt, vx, cx));                      // :187
+    const T pry = vfma(dt2, fy, vfma(dt, vy, cy));
+    const T prz = vfma(dt2, fz, vfma(dt, vz, cz));
+    const T ddx = vsub(prx, parx), ddy = vsub(pry, pary), ddz = vsub(prz, parz);   // :191-192
+    const T l = vdot3(ddx, ddy, ddz, ddx, ddy, ddz);
+    T sc;
+#pragma unroll
+    for (int i = 0; i < n; ++i) setel(sc, i, P.rest * rsqrt_fast(el(l, i)));
+    o.px = vfma(sc, ddx, parx); o.py = vfma(sc, ddy, pary); o.pz = vfma(sc, ddz, parz);
+    const T vs = bc<T>(P.vel_scale);
+    T nvx = vmul(vsub(o.px, cx), vs), nvy = vmul(vsub(o.py, cy), vs), nvz = vmul(vsub(o.pz, cz), vs);   // :195-197
+    const T l2 = vdot3(nvx, nvy, nvz, nvx, nvy, nvz);
+    bool clampv = false;
+#pragma unroll
+    for (int i = 0; i < n; ++i) clampv |= el(l2, i) > P.vmax2;
+    if (clampv) {                                                       // :198-200
+        T s;
+#pragma unroll
+        for (int i = 0; i < n; ++i) setel(s, i, el(l2, i) > P.vmax2 ? P.vmax * rsqrt_fast(el(l2, i)) : 1.0f);
+        nvx = vmul(nvx, s); nvy = vmul(nvy, s); nvz = vmul(nvz, s);
     }
     o.vx = nvx; o.vy = nvy; o.vz = nvz;
-    o.dx = P.damping * (o.px - prx); o.dy = P.damping * (o.py - pry); o.dz = P.damping * (o.pz - prz);  // :201
+    const T dmp = bc<T>(P.damping);
+    o.dx = vmul(dmp, vsub(o.px, prx)); o.dy = vmul(dmp, vsub(o.py, pry)); o.dz = vmul(dmp, vsub(o.pz, prz));  // :201
     return o;
 }
 
 // ---- K1: integrate + collide + FTL + corrected velocity -------------------------------------
-// One thread owns V consecutive strands and walks them root->tip together (V independent
-// dependency chains per thread).  Point i's velocity is final only once d_{i+1} is known
-// (compute.comp:213-215), so the velocity store trails the position by one point.
+// One thread owns V consecutive strands and walks them root->tip together.  V = 1: scalar; V = 2, 4:
+// strands are paired into fp32x2 packs (LDG.64 / LDG.128 deliver the packs directly).  Point i's
+// velocity is final only once d_{i+1} is known (compute.comp:213-215), so the velocity store trails the
+// position by one point.
+template <int V> struct PackOf { using T = float2; static constexpr int n = V / 2; };
+template <> struct PackOf<1> { using T = float; static constexpr int n = 1; };
+
+template <int V> __device__ __forceinline__ void load_packs(const float* __restrict__ p, typename PackOf<V>::T (&o)[PackOf<V>::n]) {
+    if constexpr (V == 1) { o[0] = __ldg(p); }
+    else if constexpr (V == 2) { o[0] = __ldg(reinterpret_cast<const float2*>(p)); }
+    else { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); o[0] = make_float2(t.x, t.y); o[1] = make_float2(t.z, t.w); }
+}
+template <int V> __device__ __forceinline__ void store_packs(float* __restrict__ p, const typename PackOf<V>::T (&o)[PackOf<V>::n]) {
+    if constexpr (V == 1) { *p = o[0]; }
+    else if constexpr (V == 2) { *reinterpret_cast<float2*>(p) = o[0]; }
+    else { *reinterpret_cast<float4*>(p) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y); }
+}
+
 template <int V, bool WIND, int NELL>
 __global__ void __launch_bounds__(kBlock)
 k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr) {
+    using T = typename PackOf<V>::T;
+    constexpr int NP = PackOf<V>::n;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int s0 = t * V;
-    const bool active = s0 < P.S_pad;
-    if (active) {
-        const size_t plane = (size_t)P.N * P.S_pad;
-        float* const ppx = planes + s0;
-        float* const ppy = ppx + plane;
-        float* const ppz = ppy + plane;
-        float* const pvx = ppz + plane;
-        float* const pvy = pvx + plane;
-        float* const pvz = pvy + plane;
+    if (s0 >= P.S_pad) return;
+    const size_t plane = (size_t)P.N * P.S_pad;
+    float* const ppx = planes + s0;
+    float* const ppy = ppx + plane;
+    float* const ppz = ppy + plane;
+    float* const pvx = ppz + plane;
+    float* const pvy = pvx + plane;
+    float* const pvz = pvy + plane;
 
-        float parx[V], pary[V], parz[V];
-        load_vec<V>(ppx, parx); load_vec<V>(ppy, pary); load_vec<V>(ppz, parz);
-        float nx[V], ny[V], nz[V], nvx[V], nvy[V], nvz[V];
-        {
-            const size_t o = P.S_pad;
-            load_vec<V>(ppx + o, nx); load_vec<V>(ppy + o, ny); load_vec<V>(ppz + o, nz);
-            load_vec<V>(pvx + o, nvx); load_vec<V>(pvy + o, nvy); load_vec<V>(pvz + o, nvz);
-        }
-        float lvx[V], lvy[V], lvz[V];   // clamped velocity of the previous point, correction pending
-#pragma unroll
-        for (int u = 0; u < V; ++u) { lvx[u] = 0.f; lvy[u] = 0.f; lvz[u] = 0.f; }
-
-        size_t oi = P.S_pad;
-        for (int i = 1; i < P.N; ++i, oi += P.S_pad) {
-            float cx[V], cy[V], cz[V], vx[V], vy[V], vz[V];
-#pragma unroll
-            for (int u = 0; u < V; ++u) { cx[u] = nx[u]; cy[u] = ny[u]; cz[u] = nz[u]; vx[u] = nvx[u]; vy[u] = nvy[u]; vz[u] = nvz[u]; }
-            if (i + 1 < P.N) {
-                const size_t o = oi + P.S_pad;
-                load_vec<V>(ppx + o, nx); load_vec<V>(ppy + o, ny); load_vec<V>(ppz + o, nz);
-                load_vec<V>(pvx + o, nvx); load_vec<V>(pvy + o, nvy); load_vec<V>(pvz + o, nvz);
-            }
-            float opx[V], opy[V], opz[V], fvx[V], fvy[V], fvz[V], odx[V], ody[V], odz[V];
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                const PointOut o = point_update<WIND, NELL>(P, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
-                opx[u] = o.px; opy[u] = o.py; opz[u] = o.pz;
-                odx[u] = o.dx; ody[u] = o.dy; odz[u] = o.dz;
-                // finalise point i-1: v_{i-1} -= d_i / dt   (compute.comp:213-215)
-                fvx[u] = fmaf(-o.dx, P.inv_dt, lvx[u]); fvy[u] = fmaf(-o.dy, P.inv_dt, lvy[u]); fvz[u] = fmaf(-o.dz, P.inv_dt, lvz[u]);
-                lvx[u] = o.vx; lvy[u] = o.vy; lvz[u] = o.vz;
-            }
-            store_vec<V>(ppx + oi, opx); store_vec<V>(ppy + oi, opy); store_vec<V>(ppz + oi, opz);
-            if (P.keep_corr) {
-                float* c0 = corr + s0 + oi;
-                store_vec<V>(c0, odx); store_vec<V>(c0 + plane, ody); store_vec<V>(c0 + 2 * plane, odz);
-            }
-            if (i > 1) {
-                const size_t om = oi - P.S_pad;
-                store_vec<V>(pvx + om, fvx); store_vec<V>(pvy + om, fvy); store_vec<V>(pvz + om, fvz);
-            }
-#pragma unroll
-            for (int u = 0; u < V; ++u) { parx[u] = opx[u]; pary[u] = opy[u]; parz[u] = opz[u]; }
-        }
-        // last point: no correction term (compute.comp:213 `i != NUM_CURVE_POINTS - 1`)
-        const size_t ol = (size_t)(P.N - 1) * P.S_pad;
-        store_vec<V>(pvx + ol, lvx); store_vec<V>(pvy + ol, lvy); store_vec<V>(pvz + ol, lvz);
+    T parx[NP], pary[NP], parz[NP];
+    load_packs<V>(ppx, parx); load_packs<V>(ppy, pary); load_packs<V>(ppz, parz);
+    T nx[NP], ny[NP], nz[NP], nvx[NP], nvy[NP], nvz[NP];
+    {
+        const size_t o = P.S_pad;
+        load_packs<V>(ppx + o, nx); load_packs<V>(ppy + o, ny); load_packs<V>(ppz + o, nz);
+        load_packs<V>(pvx + o, nvx); load_packs<V>(pvy + o, nvy); load_packs<V>(pvz + o, nvz);
     }
+    T lvx[NP], lvy[NP], lvz[NP];   // clamped velocity of the previous point, correction pending
+#pragma unroll
+    for (int u = 0; u < NP; ++u) { lvx[u] = bc<T>(0.f); lvy[u] = bc<T>(0.f); lvz[u] = bc<T>(0.f); }
+    const T minus_inv_dt = bc<T>(-P.inv_dt);
+
+    size_t oi = P.S_pad;
+    for (int i = 1; i < P.N; ++i, oi += P.S_pad) {
+        T cx[NP], cy[NP], cz[NP], vx[NP], vy[NP], vz[NP];
+#pragma unroll
+        for (int u = 0; u < NP; ++u) { cx[u] = nx[u]; cy[u] = ny[u]; cz[u] = nz[u]; vx[u] = nvx[u]; vy[u] = nvy[u]; vz[u] = nvz[u]; }
+        if (i + 1 < P.N) {
+            const size_t o = oi + P.S_pad;
+            load_packs<V>(ppx + o, nx); load_packs<V>(ppy + o, ny); load_packs<V>(ppz + o, nz);
+            load_packs<V>(pvx + o, nvx); load_packs<V>(pvy + o, nvy); load_packs<V>(pvz + o, nvz);
+        }
+        T fvx[NP], fvy[NP], fvz[NP], odx[NP], ody[NP], odz[NP];
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            const PointOut<T> o = point_update<T, WIND, NELL>(P, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
+            parx[u] = o.px; pary[u] = o.py; parz[u] = o.pz;
+            odx[u] = o.dx; ody[u] = o.dy; odz[u] = o.dz;
+            // finalise point i-1: v_{i-1} -= d_i / dt   (compute.comp:213-215)
+            fvx[u] = vfma(o.dx, minus_inv_dt, lvx[u]); fvy[u] = vfma(o.dy, minus_inv_dt, lvy[u]); fvz[u] = vfma(o.dz, minus_inv_dt, lvz[u]);
+            lvx[u] = o.vx; lvy[u] = o.vy; lvz[u] = o.vz;
+        }
+        store_packs<V>(ppx + oi, parx); store_packs<V>(ppy + oi, pary); store_packs<V>(ppz + oi, parz);
+        if (P.keep_corr) {
+            float* c0 = corr + s0 + oi;
+            store_packs<V>(c0, odx); store_packs<V>(c0 + plane, ody); store_packs<V>(c0 + 2 * plane, odz);
+        }
+        if (i > 1) {
+            const size_t om = oi - P.S_pad;
+            store_packs<V>(pvx + om, fvx); store_packs<V>(pvy + om, fvy); store_packs<V>(pvz + om, fvz);
+        }
+    }
+    // last point: no correction term (compute.comp:213 `i != NUM_CURVE_POINTS - 1`)
+    const size_t ol = (size_t)(P.N - 1) * P.S_pad;
+    store_packs<V>(pvx + ol, lvx); store_packs<V>(pvy + ol, lvy); store_packs<V>(pvz + ol, lvz);
 }
 
 // ---- K_splat: corrected velocities -> voxel grid (compute.comp:231-252) ----------------------------
