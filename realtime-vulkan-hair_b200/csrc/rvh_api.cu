@@ -70,6 +70,8 @@ struct rvh_ctx {
     unsigned* sort_keys = nullptr; unsigned* sort_keys_out = nullptr; int* sort_ids = nullptr;
     StepParams P;
     bool uploaded = false, colliders_set = false;
+    int splat_variant = 1;                // RVH_SPLAT_VARIANT env (experiments): 1 = two-phase register accumulation (default), 0 = REDUX
+    bool gather_pending = false;          // fgrid holds a finalized grid whose gather has not been applied to the velocities yet
     // multi-GPU
     int rank = 0, nranks = 1;
     NcclComm comm = nullptr;
@@ -122,17 +124,35 @@ void prof_collect(rvh_ctx* c) {   // caller has synchronised the stream
 }
 
 template <int V, bool WIND, int NELL>
-void launch_k1(rvh_ctx* c) {
-    k_ftl_step<V, WIND, NELL><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr);
+void launch_k1(rvh_ctx* c, bool gather) {
+    if (gather) k_ftl_step<V, WIND, NELL, true><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid);
+    else        k_ftl_step<V, WIND, NELL, false><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid);
 }
 template <int V>
-void launch_k1_v(rvh_ctx* c, bool wind) {
+void launch_k1_v(rvh_ctx* c, bool wind, bool gather) {
     const bool five = c->P.n_ell == 5;     // the reference scene's collider count gets the unrolled kernel
-    if (wind) { if (five) launch_k1<V, true, 5>(c); else launch_k1<V, true, -1>(c); }
-    else      { if (five) launch_k1<V, false, 5>(c); else launch_k1<V, false, -1>(c); }
+    if (wind) { if (five) launch_k1<V, true, 5>(c, gather); else launch_k1<V, true, -1>(c, gather); }
+    else      { if (five) launch_k1<V, false, 5>(c, gather); else launch_k1<V, false, -1>(c, gather); }
 }
 
-int do_step(rvh_ctx* ctx, float dt, float total_time, int phases) {
+int launch_gather(rvh_ctx* ctx) {
+    prof_begin(ctx, EV_K2);
+    const size_t total = (size_t)(ctx->N - 1) * (ctx->S_pad / 2);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 64);
+    k_grid_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->fgrid);
+    prof_end(ctx);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    ctx->gather_pending = false;
+    return RVH_OK;
+}
+
+// Apply a deferred gather before anything reads velocities back.
+int flush_gather(rvh_ctx* ctx) { return ctx->gather_pending ? launch_gather(ctx) : RVH_OK; }
+
+// phases: bit 0 = integrate + FTL (+ splat, all-reduce), bit 1 = grid finalize + gather.
+// lazy: leave the gather to the next step's k_ftl_step (steady-state stepping); otherwise run it now.
+int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
     if (!ctx->uploaded) return fail(ctx, RVH_ERR_STATE, "rvh_step before rvh_upload_strands_aos");
     if (!ctx->colliders_set) return fail(ctx, RVH_ERR_STATE, "rvh_step before rvh_set_colliders");
     if (!(dt > 0.f)) return fail(ctx, RVH_ERR_INVALID, "dt must be > 0");
@@ -153,17 +173,20 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases) {
             prof_end(ctx);
         }
         prof_begin(ctx, EV_K1);
+        const bool fused_gather = ctx->gather_pending;
         switch (ctx->V) {
-            case 4: launch_k1_v<4>(ctx, wind); break;
-            case 2: launch_k1_v<2>(ctx, wind); break;
-            default: launch_k1_v<1>(ctx, wind); break;
+            case 4: launch_k1_v<4>(ctx, wind, fused_gather); break;
+            case 2: launch_k1_v<2>(ctx, wind, fused_gather); break;
+            default: launch_k1_v<1>(ctx, wind, fused_gather); break;
         }
         prof_end(ctx);
+        ctx->gather_pending = false;
         ctx->launches += 1;
         CU(cudaGetLastError());
         if (grid) {
             prof_begin(ctx, EV_SPLAT);
-            k_grid_splat<<<ctx->S_pad / kSplatThreads, kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid);
+            if (ctx->splat_variant == 1) k_grid_splat<<<ctx->S_pad / kSplatThreads, kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid);
+            else k_grid_splat_redux<<<ctx->S_pad / kSplatThreads, kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid);
             prof_end(ctx);
             ctx->launches += 1;
             CU(cudaGetLastError());
@@ -180,13 +203,10 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases) {
         prof_begin(ctx, EV_FINALIZE);
         k_grid_finalize<<<(cells + 255) / 256, 256, 0, ctx->stream>>>((const long long*)ctx->grid, ctx->fgrid, cells, ctx->P.int32_wrap);
         prof_end(ctx);
-        prof_begin(ctx, EV_K2);
-        const size_t total = (size_t)(ctx->N - 1) * ctx->S_pad;
-        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 64);
-        k_grid_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->fgrid);
-        prof_end(ctx);
-        ctx->launches += 2;
+        ctx->launches += 1;
         CU(cudaGetLastError());
+        ctx->gather_pending = true;
+        if (!lazy || ctx->interop_aos) { int r = launch_gather(ctx); if (r) return r; }
     }
     if (ctx->interop_aos) {
         const int tiles = (ctx->S + kTile - 1) / kTile;
@@ -217,6 +237,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->S = cfg->num_strands; c->N = cfg->num_points;
     c->S_pad = ((c->S + 127) / 128) * 128;
     c->rank = rank; c->nranks = nranks;
+    if (const char* e = std::getenv("RVH_SPLAT_VARIANT")) c->splat_variant = std::atoi(e);
     int V = cfg->strands_per_thread;
     if (V != 1 && V != 2 && V != 4) V = c->S >= 65536 ? 2 : 1;     // measured on B200: 2 strands per thread is fastest at scale
     c->V = V;
@@ -250,6 +271,11 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     P.vmax = cfg->vmax; P.vmax2 = cfg->vmax * cfg->vmax; P.penalty_k = cfg->penalty_k;
     P.sphere_r = cfg->sphere_radius; P.sphere_r2 = cfg->sphere_radius * cfg->sphere_radius;
     P.G = cfg->grid_dim; P.h = cfg->grid_extent / (float)cfg->grid_dim;    // compute.comp:205
+    P.rh = 1.0f / P.h;
+    {   // Markstein division needs a normal h whose significand is not all ones (rvh_kernels.cuh, grid_coord)
+        uint32_t hb; std::memcpy(&hb, &P.h, 4);
+        P.div_fast = (std::isnormal(P.h) && P.h > 1e-20f && P.h < 1e20f && (hb & 0x7fffffu) != 0x7fffffu) ? 1 : 0;
+    }
     for (int k = 0; k < 3; ++k) P.origin[k] = cfg->grid_origin[k];
     P.scale = cfg->grid_scale; P.friction = cfg->friction;
     P.int32_wrap = (cfg->flags & RVH_GRID_INT32_WRAP) ? 1 : 0;
@@ -346,10 +372,12 @@ static int unpack_from_staging(rvh_ctx* ctx) {
     CU(cudaGetLastError());
     ctx->launches += reorder ? 3 : 1;
     ctx->uploaded = true;
+    ctx->gather_pending = false;          // new state: nothing of the old grid applies to it
     return RVH_OK;
 }
 
 static int pack_to_staging(rvh_ctx* ctx) {
+    { int r = flush_gather(ctx); if (r) return r; }
     const int tiles = (ctx->S + kTile - 1) / kTile;
     const size_t sm = (size_t)9 * ctx->N * (kTile + 1) * sizeof(float);
     const bool reorder = ctx->perm != nullptr && !(ctx->cfg.flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
@@ -395,13 +423,13 @@ int rvh_import_strands_fd(rvh_ctx* ctx, int fd, size_t bytes) {
 int rvh_step(rvh_ctx* ctx, float dt, float total_time) {
     if (!ctx) return RVH_ERR_INVALID;
     CU(cudaSetDevice(ctx->cfg.device));
-    return do_step(ctx, dt, total_time, 3);
+    return do_step(ctx, dt, total_time, 3, true);
 }
 
 int rvh_step_phases(rvh_ctx* ctx, float dt, float total_time, int phases) {
     if (!ctx) return RVH_ERR_INVALID;
     CU(cudaSetDevice(ctx->cfg.device));
-    return do_step(ctx, dt, total_time, phases);
+    return do_step(ctx, dt, total_time, phases, false);
 }
 
 int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out) {
@@ -411,7 +439,7 @@ int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out) 
     if (ms_out) CU(cudaEventRecord(ctx->ev_a, ctx->stream));
     float t = total_time0;
     for (int i = 0; i < n; ++i) {
-        int r = do_step(ctx, dt, t, 3);
+        int r = do_step(ctx, dt, t, 3, true);
         if (r) return r;
         t += dt;
     }
@@ -429,7 +457,7 @@ int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out) 
 int rvh_step_host(rvh_ctx* ctx, void* strands, size_t bytes, float dt, float total_time) {
     int r = rvh_upload_strands_aos(ctx, strands, bytes);
     if (r) return r;
-    r = do_step(ctx, dt, total_time, 3);
+    r = do_step(ctx, dt, total_time, 3, true);
     if (r) return r;
     return rvh_download_strands_aos(ctx, strands, bytes);
 }

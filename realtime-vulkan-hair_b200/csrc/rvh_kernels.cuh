@@ -7,6 +7,14 @@
 // 32/64/128-bit loads per plane, and the root->tip chain of a strand lives in registers.
 // The voxel grid is int64 [G^3][4] (vx,vy,vz,density), fixed point x grid_scale; integer
 // accumulation makes the result independent of atomics order and of the GPU count.
+//
+// Kernels per step (grid on):
+//   k_ftl_step<V,WIND,NELL,GATHER>  gather+friction of the PREVIOUS step's grid fused into the load
+//                                   (GATHER), then integrate + collide + FTL + corrected velocity
+//   k_grid_splat                    warp-aggregated (REDUX.SUM) integer splat, RED.64 to the grid
+//   [ncclAllReduce of the grid when sharded]
+//   k_grid_finalize                 int64 accumulators -> float4 cells (v/density) for the gather
+//   k_grid_gather                   stand-alone gather, only when state is read back before the next step
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,195 +37,13 @@ struct StepParams {
     int has_sphere, n_ell;
     Ellipsoid ell[kMaxEllipsoids];
     int G;
-    float h, origin[3], scale, friction;
+    float h, rh, origin[3], scale, friction;   // rh = RN(1/h)
+    int div_fast;                               // 1: h is a normal float whose significand is not all ones (see grid_coord)
     float dt, inv_dt, dt2, vel_scale;      // vel_scale = damping / dt
     int wind_mode;                          // 0 off, 1 = variant A (:151), 2 = variant B (:152)
-    float wind_s2T, wind_T3, wind_amp;      // 2*sin(2T); 3T; 10 (A) or 7*fbm(sinT,cosT) (B)
+    float wind_s2T, wind_T3, wind_amp;      // 2*sin(2T); 3T mod 2pi; 10 (A) or 7*fbm(sinT,cosT) (B)
     int int32_wrap, keep_corr;
 };
-
-template <int V> struct VecOf;
-template <> struct VecOf<1> { using type = float; };
-template <> struct VecOf<2> { using type = float2; };
-template <> struct VecOf<4> { using type = float4; };
-
-template <int V> __device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&o)[V]) {
-    if constexpr (V == 1) { o[0] = __ldg(p); }
-    else if constexpr (V == 2) { float2 t = __ldg(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1] = t.y; }
-    else { float4 t = __ldg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
-}
-template <int V> __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&o)[V]) {
-    if constexpr (V == 1) { *p = o[0]; }
-    else if constexpr (V == 2) { *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1]); }
-    else { *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]); }
-}
-
-// ---- per-axis cell range of a point: compute.comp:219-229 --------------------------------
-// The shader's [max(floor,0), min(floor+1,G-1)] range is exactly "cells f and f+1, each kept
-// only if it lies in [0,G-1]"; w0/w1 are clamp(1-|g-cell|,0,1) (compute.comp:237-239).
-struct AxisCells { int f; float w0, w1; bool ok0, ok1; };
-
-__device__ __forceinline__ AxisCells axis_cells(float p, float origin, float h, int G) {
-    AxisCells a;
-    const float g = __fdiv_rn(p - origin, h);
-    float fl = floorf(g);
-    fl = fminf(fmaxf(fl, -2.0f), (float)G);           // far-away / NaN points touch no cell
-    a.f = (int)fl;
-    a.w0 = __saturatef(1.0f - fabsf(g - (float)a.f));
-    a.w1 = __saturatef(1.0f - fabsf(g - (float)(a.f + 1)));
-    a.ok0 = (a.f >= 0) && (a.f <= G - 1);
-    a.ok1 = (a.f + 1 >= 0) && (a.f + 1 <= G - 1);
-    return a;
-}
-
-// ---- P2 splat: compute.comp:231-252 -----------------------------------------------------------
-// Per corner the shader adds int(SCALE * (w * v_k)) and int(SCALE * w), truncated toward zero; the float
-// operations below are ordered exactly as the shader orders them, so the integers are the reference's.
-// The accumulators are int64 (SURVEY.md section 7: int32 overflows beyond ~50K strands); integer sums are
-// order-independent, which is what makes the warp aggregation below (and the multi-GPU all-reduce) exact.
-__device__ __forceinline__ void global_add(unsigned long long* __restrict__ p, long long v) {
-    if (v) atomicAdd(p, (unsigned long long)v);                        // RED.E.ADD.64, fire and forget
-}
-
-// Slow path: one lane splats its point straight into the global grid (8 corners x 4 atomics).
-// 64-bit conversions, so |SCALE*w*v| >= 2^31 keeps its value as in the int64 oracle.
-__device__ __forceinline__ void splat_point_direct(const StepParams& P, unsigned long long* __restrict__ grid,
-                                                   const AxisCells& X, const AxisCells& Y, const AxisCells& Z,
-                                                   float vx, float vy, float vz) {
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        if (!(a ? X.ok1 : X.ok0)) continue;
-        const float xw = a ? X.w1 : X.w0;
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            if (!(b ? Y.ok1 : Y.ok0)) continue;
-            const float xyw = __fmul_rn(xw, b ? Y.w1 : Y.w0);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (!(c ? Z.ok1 : Z.ok0)) continue;
-                const float tw = __fmul_rn(xyw, c ? Z.w1 : Z.w0);
-                unsigned long long* cell = grid + 4 * (size_t)((X.f + a) + (Y.f + b) * P.G + (Z.f + c) * P.G * P.G);
-                global_add(cell + 0, __float2ll_rz(__fmul_rn(P.scale, __fmul_rn(tw, vx))));
-                global_add(cell + 1, __float2ll_rz(__fmul_rn(P.scale, __fmul_rn(tw, vy))));
-                global_add(cell + 2, __float2ll_rz(__fmul_rn(P.scale, __fmul_rn(tw, vz))));
-                global_add(cell + 3, __float2ll_rz(__fmul_rn(P.scale, tw)));
-            }
-        }
-    }
-}
-
-// Warp-aggregated splat of one ROW: lane = strand, all 32 lanes hold the same point index of 32
-// neighbouring strands.  Strands are Morton-ordered by root, so the 32 points of a row share their base
-// cell (or split over very few cells).  For every group of lanes with the same base cell the 32
-// per-lane integers (8 corners x {vx,vy,vz,density}) are summed across the warp with REDUX.SUM -- exact,
-// they are integers -- and ONE warp-wide RED.64 with 32 distinct addresses (8 cells x 32 bytes) carries the
-// group's total to the grid: 32x fewer atomics than the shader's one-atomic-per-point-per-corner scheme,
-// no shared-memory staging, no bounding boxes.
-constexpr int kSplatMaxGroups = 6;        // more distinct cells than this in one row: lanes go direct
-constexpr float kSplatAggVmax = 60.0f;    // |c| <= 6e7 per lane, so a 32-lane int32 sum cannot overflow
-
-__device__ __forceinline__ int pick_by_lane(const int (&s)[32], int lane) {
-    int t16[16], t8[8], t4[4], t2[2];
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) t16[i] = b4 ? s[i + 16] : s[i];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t8[i] = b3 ? t16[i + 8] : t16[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) t4[i] = b2 ? t8[i + 4] : t8[i];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) t2[i] = b1 ? t4[i + 2] : t4[i];
-    return b0 ? t2[1] : t2[0];
-}
-
-__device__ __forceinline__ void splat_row(const StepParams& P, unsigned long long* __restrict__ grid, int lane, bool live,
-                                          float px, float py, float pz, float vx, float vy, float vz) {
-    constexpr unsigned kFull = 0xffffffffu;
-    const AxisCells X = axis_cells(px, P.origin[0], P.h, P.G);
-    const AxisCells Y = axis_cells(py, P.origin[1], P.h, P.G);
-    const AxisCells Z = axis_cells(pz, P.origin[2], P.h, P.G);
-    const bool touches = live && (X.ok0 || X.ok1) && (Y.ok0 || Y.ok1) && (Z.ok0 || Z.ok1);
-    const float vinf = fmaxf(fabsf(vx), fmaxf(fabsf(vy), fabsf(vz)));
-    const bool fast = vinf <= kSplatAggVmax;                           // false for NaN too
-    // base-cell key; f is clamped to [-2, G] by axis_cells, so (f + 2) < G + 3
-    const int W = P.G + 3;
-    const int key = touches ? (X.f + 2) + ((Y.f + 2) + (Z.f + 2) * W) * W : -1;
-    const unsigned same = __match_any_sync(kFull, key);
-    const bool leader = touches && (lane == __ffs(same) - 1);
-    unsigned leaders = __ballot_sync(kFull, leader);
-    if (leaders == 0u) return;                                         // the whole row is outside the grid
-    if (__popc(leaders) > kSplatMaxGroups || __any_sync(kFull, touches && !fast)) {
-        if (touches) splat_point_direct(P, grid, X, Y, Z, vx, vy, vz);
-        return;
-    }
-    // the 32 integers of this lane's point, index j = corner * 4 + component, corner = a + 2b + 4c
-    int c[32];
-#pragma unroll
-    for (int cz = 0; cz < 2; ++cz)
-#pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const float tw = __fmul_rn(__fmul_rn(a ? X.w1 : X.w0, b ? Y.w1 : Y.w0), cz ? Z.w1 : Z.w0);
-                const int j = 4 * (a + 2 * b + 4 * cz);
-                c[j + 0] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vx)));
-                c[j + 1] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vy)));
-                c[j + 2] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, vz)));
-                c[j + 3] = __float2int_rz(__fmul_rn(P.scale, tw));
-            }
-    const int comp = lane & 3, ca = (lane >> 2) & 1, cb = (lane >> 3) & 1, cc = (lane >> 4) & 1;
-    while (leaders) {
-        const int L = __ffs(leaders) - 1;
-        leaders &= leaders - 1;
-        const int member = -(int)((same >> L) & 1u);                   // all-ones for the lanes of leader L's group
-        int s[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s[j] = __reduce_add_sync(kFull, c[j] & member);
-        const int mine = pick_by_lane(s, lane);
-        const int fx = __shfl_sync(kFull, X.f, L) + ca, fy = __shfl_sync(kFull, Y.f, L) + cb, fz = __shfl_sync(kFull, Z.f, L) + cc;
-        const bool ok = (unsigned)fx < (unsigned)P.G && (unsigned)fy < (unsigned)P.G && (unsigned)fz < (unsigned)P.G;
-        if (ok) global_add(grid + 4 * (size_t)(fx + (fy + fz * P.G) * P.G) + comp, (long long)mine);
-    }
-}
-
-// ---- P3 gather of one point: compute.comp:259-297 ------------------------------------------
-// fgrid[cell] = (float(vel.x), float(vel.y), float(vel.z), density > 0 ? 1/float(density) : 0),
-// prepared once per step by k_grid_finalize.  Written without FMA contraction so the result is
-// bit-identical to the C oracle when positions, velocities and grid are.
-__device__ __forceinline__ void gather_point(const StepParams& P, const float4* __restrict__ fgrid,
-                                             float px, float py, float pz, float& vx, float& vy, float& vz) {
-    const AxisCells X = axis_cells(px, P.origin[0], P.h, P.G);
-    const AxisCells Y = axis_cells(py, P.origin[1], P.h, P.G);
-    const AxisCells Z = axis_cells(pz, P.origin[2], P.h, P.G);
-    float gx = 0.f, gy = 0.f, gz = 0.f;
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        if (!(a ? X.ok1 : X.ok0)) continue;
-        const float xw = a ? X.w1 : X.w0;
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            if (!(b ? Y.ok1 : Y.ok0)) continue;
-            const float xyw = __fmul_rn(xw, b ? Y.w1 : Y.w0);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (!(c ? Z.ok1 : Z.ok0)) continue;
-                const float tw = __fmul_rn(xyw, c ? Z.w1 : Z.w0);
-                const int idx = (X.f + a) + (Y.f + b) * P.G + (Z.f + c) * P.G * P.G;
-                const float4 cell = __ldg(fgrid + idx);
-                if (cell.w > 0.f) {                                     // density > 0, compute.comp:276
-                    const float s = __fmul_rn(tw, cell.w);              // totalWeight * (1.0 / float(density))
-                    gx = __fadd_rn(gx, __fmul_rn(s, cell.x));
-                    gy = __fadd_rn(gy, __fmul_rn(s, cell.y));
-                    gz = __fadd_rn(gz, __fmul_rn(s, cell.z));
-                }
-            }
-        }
-    }
-    const float fr = P.friction, omf = __fsub_rn(1.0f, fr);
-    vx = __fadd_rn(__fmul_rn(omf, vx), __fmul_rn(fr, gx));
-    vy = __fadd_rn(__fmul_rn(omf, vy), __fmul_rn(fr, gy));
-    vz = __fadd_rn(__fmul_rn(omf, vz), __fmul_rn(fr, gz));
-}
 
 // ---- wind trigonometry ---------------------------------------------------------------------------
 // The wind force enters positions multiplied by dt^2 (2.8e-4 at 60 Hz), so MUFU.SIN/COS accuracy is far
@@ -261,6 +87,148 @@ __device__ __forceinline__ float  el(float2 a, int i) { return i ? a.y : a.x; }
 __device__ __forceinline__ void setel(float& a, int, float v)    { a = v; }
 __device__ __forceinline__ void setel(float2& a, int i, float v) { if (i) a.y = v; else a.x = v; }
 template <class T> __device__ __forceinline__ T vdot3(T ax, T ay, T az, T bx, T by, T bz) { return vfma(ax, bx, vfma(ay, by, vmul(az, bz))); }
+
+// ---- grid coordinates of a point: compute.comp:219-229, 237-239 ---------------------------------
+// g = (p - origin) / h must be the IEEE quotient: the integer grid is compared bit for bit with the
+// oracle, and floor(g) decides the cell.  x / h is evaluated as Markstein's sequence around the
+// host-rounded reciprocal rh = RN(1/h):
+//     q0 = x*rh;  q1 = q0 + (x - h*q0)*rh;  q2 = q1 + (x - h*q1)*rh
+// q1 is within one ulp, so q2 = RN(x/h) whenever the significand of h is not all ones and nothing
+// under/overflows (checked EXHAUSTIVELY over all 2^32 floats x against x/h for six cell sizes,
+// zero mismatches for 1e-30 <= |x| <= 1e30; outside that range the weights / the
+// no-cell outcome are identical anyway).  Five packed FFMA2/FMUL2 for two divisions instead of two
+// MUFU.RCP + FCHK + branch sequences.  div_fast = 0 selects plain division.
+template <class T>
+__device__ __forceinline__ T grid_coord(const StepParams& P, T p, int axis) {
+    const T x = vsub(p, bc<T>(P.origin[axis]));
+    if (P.div_fast) {
+        const T rh = bc<T>(P.rh), mh = bc<T>(-P.h);
+        const T q0 = vmul(x, rh);
+        const T q1 = vfma(vfma(mh, q0, x), rh, q0);
+        return vfma(vfma(mh, q1, x), rh, q1);
+    }
+    T g;
+#pragma unroll
+    for (int i = 0; i < VecTraits<T>::n; ++i) setel(g, i, __fdiv_rn(el(x, i), P.h));
+    return g;
+}
+
+// The shader's [max(floor,0), min(floor+1,G-1)] cell range is exactly "cells f and f+1, each kept only
+// if it lies in [0,G-1]".  Weights clamp(1-|g-cell|,0,1): for cell f, g-f is in [0,1) so the weight is
+// 1-(g-f); for cell f+1, g-(f+1) is in [-1,0) so it is 1+(g-(f+1)); same roundings as the shader's
+// expression, no abs / clamp needed.  f is clamped to [-2, G] first (far-away / NaN points: no valid cell).
+template <class T> struct AxisCells { T w0, w1; int f[VecTraits<T>::n]; };
+
+template <class T>
+__device__ __forceinline__ AxisCells<T> axis_cells(const StepParams& P, T p, int axis) {
+    constexpr int n = VecTraits<T>::n;
+    AxisCells<T> a;
+    const T g = grid_coord<T>(P, p, axis);
+    T fl;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        const float f = fminf(fmaxf(floorf(el(g, i)), -2.0f), (float)P.G);
+        setel(fl, i, f);
+        a.f[i] = (int)f;
+    }
+    a.w0 = vfma(vsub(g, fl), bc<T>(-1.0f), bc<T>(1.0f));
+    a.w1 = vadd(vsub(g, vadd(fl, bc<T>(1.0f))), bc<T>(1.0f));
+    return a;
+}
+__device__ __forceinline__ bool cell_ok(int f, int G) { return (unsigned)f < (unsigned)G; }
+
+// ---- P2 splat: compute.comp:231-252 -----------------------------------------------------------
+// Per corner the shader adds int(SCALE * (w * v_k)) and int(SCALE * w), truncated toward zero; the float
+// operations below are ordered exactly as the shader orders them, so the integers are the reference's.
+// The accumulators are int64 (SURVEY.md section 7: int32 overflows beyond ~50K strands); integer sums are
+// order-independent, which is what makes the warp aggregation below (and the multi-GPU all-reduce) exact.
+__device__ __forceinline__ void global_add(unsigned long long* __restrict__ p, long long v) {
+    if (v) atomicAdd(p, (unsigned long long)v);                        // RED.E.ADD.64, fire and forget
+}
+
+// Slow path: one lane splats ONE point straight into the global grid (8 corners x 4 atomics).
+// 64-bit conversions, so |SCALE*w*v| >= 2^31 keeps its value as in the int64 oracle.
+__device__ __forceinline__ void splat_point_direct(const StepParams& P, unsigned long long* __restrict__ grid,
+                                                   int fx, int fy, int fz, const float (&wx)[2], const float (&wy)[2], const float (&wz)[2],
+                                                   float vx, float vy, float vz) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        if (!cell_ok(fx + a, P.G)) continue;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            if (!cell_ok(fy + b, P.G)) continue;
+            const float xyw = __fmul_rn(wx[a], wy[b]);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (!cell_ok(fz + c, P.G)) continue;
+                const float tw = __fmul_rn(xyw, wz[c]);
+                unsigned long long* cell = grid + 4 * (size_t)((fx + a) + ((fy + b) + (fz + c) * P.G) * P.G);
+                global_add(cell + 0, __float2ll_rz(__fmul_rn(P.scale, __fmul_rn(tw, vx))));
+                global_add(cell + 1, __float2ll_rz(__fmul_rn(P.scale, __fmul_rn(tw, vy))));
+                global_add(cell + 2, __float2ll_rz(__fmul_rn(P.scale, __fmul_rn(tw, vz))));
+                global_add(cell + 3, __float2ll_rz(__fmul_rn(P.scale, tw)));
+            }
+        }
+    }
+}
+
+// ---- P3 gather + friction of one pack: compute.comp:259-297 ---------------------------------------
+// fgrid[cell] = (vx, vy, vz) / density as floats (zero where density <= 0), prepared once per step by
+// k_grid_finalize, so a corner costs one LDG.128 and three FMAs (one FFMA2 + one FFMA).  Floating point:
+// agrees with the shader's  w * (1/d) * v  to a few ulp (tolerance-checked, not bit-compared).
+template <class T>
+__device__ __forceinline__ void gather_pack(const StepParams& P, const float4* __restrict__ fgrid, T px, T py, T pz, T& vx, T& vy, T& vz) {
+    constexpr int n = VecTraits<T>::n;
+    const AxisCells<T> X = axis_cells<T>(P, px, 0), Y = axis_cells<T>(P, py, 1), Z = axis_cells<T>(P, pz, 2);
+    float2 gxy[n]; float gz[n];
+    bool interior = true;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        gxy[i] = make_float2(0.f, 0.f); gz[i] = 0.f;
+        interior = interior && cell_ok(X.f[i], P.G - 1) && cell_ok(Y.f[i], P.G - 1) && cell_ok(Z.f[i], P.G - 1);
+    }
+    const T xy[4] = { vmul(X.w0, Y.w0), vmul(X.w1, Y.w0), vmul(X.w0, Y.w1), vmul(X.w1, Y.w1) };
+    if (interior) {                                                     // all 8 corners of every point are cells
+        const float4* base[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) base[i] = fgrid + (X.f[i] + (Y.f[i] + Z.f[i] * P.G) * P.G);
+        const int sy = P.G, sz = P.G * P.G;
+#pragma unroll
+        for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+            for (int ab = 0; ab < 4; ++ab) {
+                const T tw = vmul(xy[ab], cz ? Z.w1 : Z.w0);
+                const int off = (ab & 1) + (ab >> 1) * sy + cz * sz;
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const float4 cell = __ldg(base[i] + off);
+                    const float w = el(tw, i);
+                    gxy[i] = __ffma2_rn(make_float2(w, w), make_float2(cell.x, cell.y), gxy[i]);
+                    gz[i] = fmaf(w, cell.z, gz[i]);
+                }
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+                for (int ab = 0; ab < 4; ++ab) {
+                    const int fx = X.f[i] + (ab & 1), fy = Y.f[i] + (ab >> 1), fz = Z.f[i] + cz;
+                    if (cell_ok(fx, P.G) && cell_ok(fy, P.G) && cell_ok(fz, P.G)) {
+                        const float4 cell = __ldg(fgrid + (fx + (fy + fz * P.G) * P.G));
+                        const float w = el(xy[ab], i) * el(cz ? Z.w1 : Z.w0, i);
+                        gxy[i] = __ffma2_rn(make_float2(w, w), make_float2(cell.x, cell.y), gxy[i]);
+                        gz[i] = fmaf(w, cell.z, gz[i]);
+                    }
+                }
+    }
+    T gx, gy, gzz;
+#pragma unroll
+    for (int i = 0; i < n; ++i) { setel(gx, i, gxy[i].x); setel(gy, i, gxy[i].y); setel(gzz, i, gz[i]); }
+    const T fr = bc<T>(P.friction), omf = bc<T>(1.0f - P.friction);     // :296-297
+    vx = vfma(fr, gx, vmul(omf, vx)); vy = vfma(fr, gy, vmul(omf, vy)); vz = vfma(fr, gzz, vmul(omf, vz));
+}
 
 // ---- P1 for one point (or one pack of two): compute.comp:144-201 --------------------------------
 template <class T> struct PointOut { T px, py, pz, vx, vy, vz, dx, dy, dz; };
@@ -426,9 +394,13 @@ template <int V> __device__ __forceinline__ void store_packs(float* __restrict__
     else { *reinterpret_cast<float4*>(p) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y); }
 }
 
-template <int V, bool WIND, int NELL>
+// GATHER: the previous step's grid gather + friction (compute.comp:257-298) is applied to each velocity
+// as it is loaded -- the same positions and the same fgrid the stand-alone k_grid_gather would use -- so
+// the per-step K2 pass (re-read p,v, re-write v: 36 B/point) disappears from steady-state stepping.
+template <int V, bool WIND, int NELL, bool GATHER>
 __global__ void __launch_bounds__(kBlock)
-k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr) {
+k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr,
+           const float4* __restrict__ fgrid) {
     using T = typename PackOf<V>::T;
     constexpr int NP = PackOf<V>::n;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -468,6 +440,7 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
         T fvx[NP], fvy[NP], fvz[NP], odx[NP], ody[NP], odz[NP];
 #pragma unroll
         for (int u = 0; u < NP; ++u) {
+            if (GATHER) gather_pack<T>(P, fgrid, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u]);
             const PointOut<T> o = point_update<T, WIND, NELL>(P, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
             parx[u] = o.px; pary[u] = o.py; parz[u] = o.pz;
             odx[u] = o.dx; ody[u] = o.dy; odz[u] = o.dz;
@@ -491,37 +464,226 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
 }
 
 // ---- K_splat: corrected velocities -> voxel grid (compute.comp:231-252) ----------------------------
-// One warp owns 32 consecutive strands and walks their rows root->tip: every load is a fully coalesced
-// 128-byte row segment of a plane, the next row is in flight while the current one is aggregated
-// (splat_row above).  Grid sized to the strand count; no shared memory.
+// The shader issues 32 integer atomics per point (8 corners x {vx,vy,vz,density}).  Here a warp owns 32
+// neighbouring strands (Morton-ordered by root, so the 32 points of a row share their base cell or
+// split over very few cells) and walks the rows root->tip in two phases per row:
+//   A  lane = strand: coalesced 128-byte loads of the row (next row already in flight), exact grid
+//      coordinates, per-axis weights and the base-cell key, staged in shared memory (points moving
+//      faster than the int32 bound go straight to the grid on their own);
+//   B  lane = (corner, slot): the 32 lanes are the 8 corners x 4 slots; in 4 iterations each lane
+//      turns two (point, corner) pairs -- one fp32x2 pack -- into their four integers each, float
+//      operations ordered exactly as the shader orders them (FMUL2, then F2I.TRUNC), and adds them into
+//      the REGISTER accumulators of K0 or K1.  No atomic, no shuffle, no divergence.
+// At the end of the row each of the (at most two) cells is finished by a 12-instruction reduce-scatter
+// across the 4 slots and ONE warp-wide RED.64 with 32 distinct addresses (8 cells x 32 bytes).  Integer
+// sums are exact in any order, so the grid equals the shader's bit for bit, with 32x fewer atomics and
+// no shared-memory atomics or bounding boxes.
 constexpr int kSplatThreads = 128;
+constexpr float kSplatAggVmax = 60.0f;    // |c| <= 6e7 per contribution, 8 per lane, 4 lanes per corner: < 2^31
+constexpr int kStageW = 40;                // words between the a=0 and a=1 weight rows: distinct banks for LDS.64
+
+struct SplatStage {                        // one row of one warp
+    float w[3][2][kStageW];                // [axis][cell f / f+1][point]
+    float v[3][32];                        // [component][point]
+    int key[32];                           // base-cell key, -1 = nothing to add
+};
+
+__device__ __forceinline__ int splat_key(int fx, int fy, int fz) {       // f in [-2, G], G <= 1024: 11 bits each
+    return (fx + 2) | ((fy + 2) << 11) | ((fz + 2) << 22);
+}
+
+// Sum the accumulators of one cell over the 4 slots of each corner (lanes l, l^8, l^16, l^24) so that the lane
+// ends up with ONE component of its corner, then add it to the grid: one RED.64 per lane, 32 distinct addresses.
+__device__ __forceinline__ void splat_flush_cell(const StepParams& P, unsigned long long* __restrict__ grid, int lane, int key,
+                                                 int a0, int a1, int a2, int a3) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const bool hi = lane & 16, mid = lane & 8;
+    int k0 = hi ? a2 : a0, k1 = hi ? a3 : a1;
+    k0 += __shfl_xor_sync(kFull, hi ? a0 : a2, 16);
+    k1 += __shfl_xor_sync(kFull, hi ? a1 : a3, 16);
+    int mine = mid ? k1 : k0;
+    mine += __shfl_xor_sync(kFull, mid ? k0 : k1, 8);
+    const int comp = (hi ? 2 : 0) + (mid ? 1 : 0);
+    const int fx = (key & 2047) - 2 + (lane & 1), fy = ((key >> 11) & 2047) - 2 + ((lane >> 1) & 1), fz = (key >> 22) - 2 + ((lane >> 2) & 1);
+    if (cell_ok(fx, P.G) && cell_ok(fy, P.G) && cell_ok(fz, P.G))
+        global_add(grid + 4 * (size_t)(fx + (fy + fz * P.G) * P.G) + comp, (long long)mine);
+}
 
 __global__ void __launch_bounds__(kSplatThreads)
 k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid) {
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * kSplatThreads + threadIdx.x;           // S_pad is a multiple of 128: always in bounds
+    constexpr unsigned kFull = 0xffffffffu;
+    __shared__ __align__(16) SplatStage stage[kSplatThreads / 32][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x * kSplatThreads + threadIdx.x;            // S_pad is a multiple of 128: always in bounds
     const bool live = s < P.S;
-    if (!__any_sync(0xffffffffu, live)) return;
+    if (!__any_sync(kFull, live)) return;
+    const int ca = lane & 1, cb = (lane >> 1) & 1, cc = (lane >> 2) & 1, slot = lane >> 3;
     const size_t plane = (size_t)P.N * P.S_pad;
     const float* p0 = planes + s;
-    float n[6];
+    float nx[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) n[k] = __ldg(p0 + k * plane + P.S_pad);
+    for (int k = 0; k < 6; ++k) nx[k] = __ldg(p0 + k * plane + P.S_pad);
+    size_t o = P.S_pad;
+    const float2 sc2 = make_float2(P.scale, P.scale);
+    for (int r = 1; r < P.N; ++r) {
+        float c[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c[k] = nx[k];
+        o += P.S_pad;
+        if (r + 1 < P.N) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) nx[k] = __ldg(p0 + k * plane + o);
+        }
+        // ---- phase A: lane = strand -------------------------------------------------------------------
+        const AxisCells<float> X = axis_cells<float>(P, c[0], 0), Y = axis_cells<float>(P, c[1], 1), Z = axis_cells<float>(P, c[2], 2);
+        const bool touches = live && (cell_ok(X.f[0], P.G) || cell_ok(X.f[0] + 1, P.G)) && (cell_ok(Y.f[0], P.G) || cell_ok(Y.f[0] + 1, P.G)) &&
+                             (cell_ok(Z.f[0], P.G) || cell_ok(Z.f[0] + 1, P.G));
+        const float vinf = fmaxf(fabsf(c[3]), fmaxf(fabsf(c[4]), fabsf(c[5])));
+        int key = (touches && vinf <= kSplatAggVmax) ? splat_key(X.f[0], Y.f[0], Z.f[0]) : -1;
+        if (touches && key == -1) {                                     // very fast (or NaN) point: 64-bit path, on its own
+            const float wx[2] = { X.w0, X.w1 }, wy[2] = { Y.w0, Y.w1 }, wz[2] = { Z.w0, Z.w1 };
+            splat_point_direct(P, grid, X.f[0], Y.f[0], Z.f[0], wx, wy, wz, c[3], c[4], c[5]);
+        }
+        unsigned rem = __ballot_sync(kFull, key != -1);
+        if (rem == 0u) continue;                                        // nothing of this row lands in the grid (warp-uniform)
+        SplatStage& st = stage[warp][r & 1];
+        st.w[0][0][lane] = X.w0; st.w[0][1][lane] = X.w1; st.w[1][0][lane] = Y.w0; st.w[1][1][lane] = Y.w1;
+        st.w[2][0][lane] = Z.w0; st.w[2][1][lane] = Z.w1;
+        st.v[0][lane] = c[3]; st.v[1][lane] = c[4]; st.v[2][lane] = c[5];
+        st.key[lane] = key;
+        __syncwarp();
+        // ---- phase B: lane = (corner, slot); pack = points (8*it + 2*slot, +1) ----------------------------
+        // two cells of the row per pass (one pass is the rule; a row that straddles more cells takes another)
+        while (rem) {
+        const int K0 = __shfl_sync(kFull, key, __ffs(rem) - 1);
+        rem &= ~__ballot_sync(kFull, key == K0);
+        int K1 = -1;
+        if (rem) { K1 = __shfl_sync(kFull, key, __ffs(rem) - 1); rem &= ~__ballot_sync(kFull, key == K1); }
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;          // cell K0
+        int e0 = 0, e1 = 0, e2 = 0, e3 = 0;          // cell K1
+        const float2* wxp = reinterpret_cast<const float2*>(st.w[0][ca]);
+        const float2* wyp = reinterpret_cast<const float2*>(st.w[1][cb]);
+        const float2* wzp = reinterpret_cast<const float2*>(st.w[2][cc]);
+        const float2* vxp = reinterpret_cast<const float2*>(st.v[0]);
+        const float2* vyp = reinterpret_cast<const float2*>(st.v[1]);
+        const float2* vzp = reinterpret_cast<const float2*>(st.v[2]);
+        const int2* kp = reinterpret_cast<const int2*>(st.key);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int i2 = 4 * it + slot;
+            const float2 tw = __fmul2_rn(__fmul2_rn(wxp[i2], wyp[i2]), wzp[i2]);
+            const float2 cx = __fmul2_rn(sc2, __fmul2_rn(tw, vxp[i2]));
+            const float2 cy = __fmul2_rn(sc2, __fmul2_rn(tw, vyp[i2]));
+            const float2 cz = __fmul2_rn(sc2, __fmul2_rn(tw, vzp[i2]));
+            const float2 cd = __fmul2_rn(sc2, tw);
+            const int2 k = kp[i2];
+            // key -1 points may carry garbage weights: they match neither K0 nor K1 (both != -1 when used)
+            const int ix0 = __float2int_rz(cx.x), iy0 = __float2int_rz(cy.x), iz0 = __float2int_rz(cz.x), id0 = __float2int_rz(cd.x);
+            const int ix1 = __float2int_rz(cx.y), iy1 = __float2int_rz(cy.y), iz1 = __float2int_rz(cz.y), id1 = __float2int_rz(cd.y);
+            if (k.x == K0) { a0 += ix0; a1 += iy0; a2 += iz0; a3 += id0; }
+            if (k.y == K0) { a0 += ix1; a1 += iy1; a2 += iz1; a3 += id1; }
+            if (K1 != -1) {
+                if (k.x == K1) { e0 += ix0; e1 += iy0; e2 += iz0; e3 += id0; }
+                if (k.y == K1) { e0 += ix1; e1 += iy1; e2 += iz1; e3 += id1; }
+            }
+        }
+        // ---- end of row: accumulators -> grid ---------------------------------------------------------
+        splat_flush_cell(P, grid, lane, K0, a0, a1, a2, a3);
+        if (K1 != -1) splat_flush_cell(P, grid, lane, K1, e0, e1, e2, e3);
+        }
+    }
+}
+
+// ---- K_splat, REDUX variant ---------------------------------------------------------------------------
+// lane = strand throughout: each lane turns its point into the 32 integers, every distinct base cell of the
+// row is summed across the warp with 32 REDUX.SUM (members masked in), each lane picks the sum of its own
+// (corner, component) with a 5-level select tree and one warp-wide RED.64 goes to the grid.
+__device__ __forceinline__ int pick_by_lane(const int (&s)[32], int lane) {
+    int t16[16], t8[8], t4[4], t2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t16[i] = b4 ? s[i + 16] : s[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t8[i] = b3 ? t16[i + 8] : t16[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t4[i] = b2 ? t8[i + 4] : t8[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) t2[i] = b1 ? t4[i + 2] : t4[i];
+    return b0 ? t2[1] : t2[0];
+}
+
+__global__ void __launch_bounds__(kSplatThreads)
+k_grid_splat_redux(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * kSplatThreads + threadIdx.x;
+    const bool live = s < P.S;
+    if (!__any_sync(kFull, live)) return;
+    const int comp = lane & 3, ca = (lane >> 2) & 1, cb = (lane >> 3) & 1, cc = (lane >> 4) & 1;   // j = comp + 4*(a + 2b + 4c)
+    const size_t plane = (size_t)P.N * P.S_pad;
+    const float* p0 = planes + s;
+    float nx[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) nx[k] = __ldg(p0 + k * plane + P.S_pad);
     size_t o = P.S_pad;
     for (int r = 1; r < P.N; ++r) {
         float c[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) c[k] = n[k];
+        for (int k = 0; k < 6; ++k) c[k] = nx[k];
         o += P.S_pad;
         if (r + 1 < P.N) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) n[k] = __ldg(p0 + k * plane + o);
+            for (int k = 0; k < 6; ++k) nx[k] = __ldg(p0 + k * plane + o);
         }
-        splat_row(P, grid, lane, live, c[0], c[1], c[2], c[3], c[4], c[5]);
+        const AxisCells<float> X = axis_cells<float>(P, c[0], 0), Y = axis_cells<float>(P, c[1], 1), Z = axis_cells<float>(P, c[2], 2);
+        const bool touches = live && (cell_ok(X.f[0], P.G) || cell_ok(X.f[0] + 1, P.G)) && (cell_ok(Y.f[0], P.G) || cell_ok(Y.f[0] + 1, P.G)) &&
+                             (cell_ok(Z.f[0], P.G) || cell_ok(Z.f[0] + 1, P.G));
+        const float vinf = fmaxf(fabsf(c[3]), fmaxf(fabsf(c[4]), fabsf(c[5])));
+        int key = (touches && vinf <= kSplatAggVmax) ? splat_key(X.f[0], Y.f[0], Z.f[0]) : -1;
+        if (touches && key == -1) {
+            const float wx[2] = { X.w0, X.w1 }, wy[2] = { Y.w0, Y.w1 }, wz[2] = { Z.w0, Z.w1 };
+            splat_point_direct(P, grid, X.f[0], Y.f[0], Z.f[0], wx, wy, wz, c[3], c[4], c[5]);
+        }
+        unsigned rem = __ballot_sync(kFull, key != -1);
+        if (rem == 0u) continue;
+        int v[32];
+#pragma unroll
+        for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const float tw = __fmul_rn(__fmul_rn(a ? X.w1 : X.w0, b ? Y.w1 : Y.w0), cz ? Z.w1 : Z.w0);
+                    const int j = 4 * (a + 2 * b + 4 * cz);
+                    v[j + 0] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, c[3])));
+                    v[j + 1] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, c[4])));
+                    v[j + 2] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, c[5])));
+                    v[j + 3] = __float2int_rz(__fmul_rn(P.scale, tw));
+                }
+        while (rem) {
+            const int K = __shfl_sync(kFull, key, __ffs(rem) - 1);
+            const bool in = key == K;
+            const unsigned grp = __ballot_sync(kFull, in);
+            rem &= ~grp;
+            int sum[32];
+            if (grp == kFull) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] = __reduce_add_sync(kFull, v[j]);
+            } else {
+                const int m = in ? -1 : 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] = __reduce_add_sync(kFull, v[j] & m);
+            }
+            const int mine = pick_by_lane(sum, lane);
+            const int fx = (K & 2047) - 2 + ca, fy = ((K >> 11) & 2047) - 2 + cb, fz = (K >> 22) - 2 + cc;
+            if (cell_ok(fx, P.G) && cell_ok(fy, P.G) && cell_ok(fz, P.G))
+                global_add(grid + 4 * (size_t)(fx + (fy + fz * P.G) * P.G) + comp, (long long)mine);
+        }
     }
 }
 
 // ---- grid finalize: int64 accumulators -> float cells for the gather ---------------------------
+// cell = (float(vel) * (1 / float(density))) per component, zero where density <= 0 (compute.comp:276-286).
 __global__ void __launch_bounds__(256)
 k_grid_finalize(const long long* __restrict__ grid, float4* __restrict__ fgrid, int cells, int int32_wrap) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -532,24 +694,28 @@ k_grid_finalize(const long long* __restrict__ grid, float4* __restrict__ fgrid, 
     if (int32_wrap) { dens = (int)dens; v0 = (int)v0; v1 = (int)v1; v2 = (int)v2; }   // the reference's int32 GridCell
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (dens > 0) {
-        o.x = __ll2float_rn(v0); o.y = __ll2float_rn(v1); o.z = __ll2float_rn(v2);
-        o.w = __frcp_rn(__ll2float_rn(dens));                    // 1.0 / float(density), compute.comp:283
+        const float rd = __frcp_rn(__ll2float_rn(dens));                 // 1.0 / float(density), compute.comp:283
+        o.x = __ll2float_rn(v0) * rd; o.y = __ll2float_rn(v1) * rd; o.z = __ll2float_rn(v2) * rd; o.w = rd;
     }
     fgrid[k] = o;
 }
 
-// ---- K2: grid gather + friction, one thread per point -------------------------------------
+// ---- K2: stand-alone grid gather + friction ------------------------------------------------------
+// Normally the gather of step k rides in k_ftl_step of step k+1; this kernel applies it when the state
+// is read back (download / interop pack) or a phase is requested explicitly.  One thread = one pack.
 __global__ void __launch_bounds__(256)
 k_grid_gather(const __grid_constant__ StepParams P, float* __restrict__ planes, const float4* __restrict__ fgrid) {
     const size_t plane = (size_t)P.N * P.S_pad;
-    const size_t total = (size_t)(P.N - 1) * P.S_pad;
+    const size_t half = (size_t)P.S_pad / 2;
+    const size_t total = (size_t)(P.N - 1) * half;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
-        const int s = (int)(k % P.S_pad);
-        if (s >= P.S) continue;
-        const size_t o = k + P.S_pad;   // skip the root row
-        float vx = planes[3 * plane + o], vy = planes[4 * plane + o], vz = planes[5 * plane + o];
-        gather_point(P, fgrid, planes[o], planes[plane + o], planes[2 * plane + o], vx, vy, vz);
-        planes[3 * plane + o] = vx; planes[4 * plane + o] = vy; planes[5 * plane + o] = vz;
+        const size_t row = k / half, s0 = 2 * (k - row * half);
+        if (s0 >= (size_t)P.S) continue;
+        float* q = planes + (row + 1) * P.S_pad + s0;   // skip the root row
+        const float2 px = *reinterpret_cast<const float2*>(q), py = *reinterpret_cast<const float2*>(q + plane), pz = *reinterpret_cast<const float2*>(q + 2 * plane);
+        float2 vx = *reinterpret_cast<const float2*>(q + 3 * plane), vy = *reinterpret_cast<const float2*>(q + 4 * plane), vz = *reinterpret_cast<const float2*>(q + 5 * plane);
+        gather_pack<float2>(P, fgrid, px, py, pz, vx, vy, vz);
+        *reinterpret_cast<float2*>(q + 3 * plane) = vx; *reinterpret_cast<float2*>(q + 4 * plane) = vy; *reinterpret_cast<float2*>(q + 5 * plane) = vz;
     }
 }
 

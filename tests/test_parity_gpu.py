@@ -146,7 +146,7 @@ def test_synthetic_head_one_step_vs_oracle(S, N, L, flags):
 # ---- integer grid: exact when fed identical inputs -------------------------------------------
 
 @pytest.mark.parametrize("S,N,L", [(900, 10, 2.5), (6000, 32, 2.5), (30000, 16, 0.4)])
-def test_grid_splat_and_gather_bit_exact_given_same_inputs(S, N, L):
+def test_grid_splat_bit_exact_and_gather_within_ulps_given_same_inputs(S, N, L):
     cols = rvh.scenes.bench_colliders()
     st = synth(S, N, L, seed_vel=5)
     rest = np.float32(L) / np.float32(N - 1)
@@ -164,8 +164,12 @@ def test_grid_splat_and_gather_bit_exact_given_same_inputs(S, N, L):
     assert np.all(mid[:, 2] == 0)
     _, ref_grid = orc.phase_splat(p, DT, mid)     # zero corr => velocities unchanged, pure splat
     assert np.array_equal(grid, ref_grid), "grid integers differ: %d cells" % int(np.any(grid != ref_grid, axis=1).sum())
+    # the gather is floating point: the CUDA path pre-divides cell velocity by density and uses FMAs, so it agrees
+    # with the shader's w * (1/d) * v evaluation order to a few ulp of the cell velocity, not bit for bit
     ref_post = orc.phase_gather(p, mid, grid)
-    assert np.array_equal(bits(post[:, 1]), bits(ref_post[:, 1])), "gathered velocities not bit-exact"
+    gerr = np.abs(post[:, 1, :, :3] - ref_post[:, 1, :, :3])
+    assert np.all(gerr <= 2e-6 * (np.abs(ref_post[:, 1, :, :3]) + np.abs(mid[:, 1, :, :3]) + 1.0)), "gather error %.3e" % gerr.max()
+    assert np.all(post[:, 1, :, 3] == 0)
     assert np.array_equal(bits(post[:, 0]), bits(mid[:, 0]))
     assert grid[:, 3].sum() > 0
 
