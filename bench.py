@@ -6,10 +6,15 @@
 N>1 is launched by torchrun (one rank per GPU); strands are sharded across ranks (weak scaling:
 every rank owns `S` strands) and the voxel grid is all-reduced with NCCL once per step.
 Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for what each field means.
+
+--impl reference times the reference's own compute.comp text (oracle/_ref: the shader compiled as C++
+against the reference's vendored glm, see oracle/ref_build/) on the host cores, one process per core; if
+oracle/_ref is not there it falls back to the OpenMP C port (oracle/oracle.c) and says so.
 """
 import argparse
 import ctypes as C
 import json
+import multiprocessing as mp
 import os
 import statistics
 import subprocess
@@ -21,8 +26,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 DT = float(np.float32(1.0 / 60.0))
+UNIT = "strand-point updates/s"
 
 # name -> (strands per GPU, points, strand length, flags, description)
 WORKLOADS = {
@@ -49,129 +56,159 @@ def parse_flags(rvh, s):
 
 
 def bytes_per_strand(N, grid):
-    """Algorithmic bytes per strand per step (fp32 xyz only): K1 reads p,v of N-1 points +
-    root p and writes p,v of N-1 points; with the grid K2 re-reads p,v and re-writes v."""
+    """Algorithmic bytes per strand per step (fp32 xyz only; SURVEY.md 8d / DESIGN.md): K1 reads p,v of N-1 points +
+    root p and writes p,v of N-1 points; the reference-shaped full step re-reads p,v and re-writes v for the gather."""
     b1 = 48 * (N - 1) + 12
     b2 = 36 * (N - 1)
     return b1, (b2 if grid else 0)
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region: NVML polled every ~2 ms from a thread (the timed region is
+    tens of milliseconds, too short for `nvidia-smi -lms`); falls back to one nvidia-smi query."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples, self.reasons, self.power = [], set(), []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+
+    def _poll(self):
+        import pynvml as nv
+        h = self.h
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[0].isdigit() else self.gpu
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.thread = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        if self.thread is None:
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for i, nm in enumerate(names):
-                if f[5 + i].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "samples": 1, "reasons": [], "how": "nvidia-smi after the run (NVML unavailable)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock query unavailable"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": sorted(self.reasons),
+                "power_w_max": max(self.power) if self.power else None, "how": "NVML polled every 2 ms during the timed region"}
 
 
-def cpu_baseline(workload, flags_s, seconds=12.0, max_steps=4, sample_strands=131072):
-    """The CPU oracle (oracle/liboracle.so, OpenMP over all host threads) on a bounded sample of
-    the same workload.  Reported beside the GPU number; never on the product path."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+# ---- the reference on the host cores ----------------------------------------------------------------------
+
+def _ref_tag(N, flags_s):
+    import orc
+    tag = "N%d%s" % (N, "_windB" if "windB" in flags_s else ("_windA" if "windA" in flags_s else ""))
+    return tag if orc.ref_available(tag) else None
+
+
+def _ref_worker(tag, S, N, L, first, steps, warmup, barrier, q):
+    """One process = one host core = one dispatch stream of the reference shader text over its own strands."""
+    import orc
+    import rvh_b200 as rvh
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, L, first_strand=first, colliders=cols)
+    for w in range(warmup):
+        st, _, _ = orc.ref_dispatch(tag, st, cols, DT, DT * w)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        st, _, _ = orc.ref_dispatch(tag, st, cols, DT, DT * (warmup + k))
+    el = time.perf_counter() - t0
+    q.put(el)
+
+
+def time_reference(workload, flags_s, steps, warmup, strands_per_proc=8192):
+    """Times the reference's CPU implementation of the path on a bounded sample.  Returns (value, info dict)."""
     import orc
     import rvh_b200 as rvh
     S_full, N, L, _, _ = WORKLOADS[workload]
-    S = min(S_full, sample_strands)
+    cores = os.cpu_count() or 1
+    tag = _ref_tag(N, flags_s) if abs(L - 2.5) < 1e-6 else None      # the shader hard-codes strand length 2.5 (compute.comp:139)
+    if tag is not None:
+        # the shader TU keeps its buffers in globals, so each core runs its own process over its own strand range; the
+        # grid is per process (as if the head were dispatched in `cores` independent pieces): same arithmetic per point
+        procs = []
+        ctx = mp.get_context("fork")
+        q, bar = ctx.Queue(), ctx.Barrier(cores)
+        for i in range(cores):
+            p = ctx.Process(target=_ref_worker, args=(tag, strands_per_proc, N, L, i * strands_per_proc, steps, warmup, bar, q))
+            p.start()
+            procs.append(p)
+        els = [q.get() for _ in procs]
+        for p in procs:
+            p.join()
+        el = max(els)
+        S = strands_per_proc * cores
+        info = {"kind": "reference", "cores": cores,
+                "sample": "%d strands x %d points per step (%d per core), %d steps: the reference's compute.comp text compiled as C++ against its vendored glm "
+                          "(oracle/_ref/libref_compute_%s.so), one process per host core, -O2, no Vulkan/lavapipe in this image" % (S, N, strands_per_proc, steps, tag)}
+        return S * N * steps / el, el, info
+    # fall back to the OpenMP C port
+    S = min(S_full, 131072)
     cols = rvh.scenes.bench_colliders()
     st = rvh.scenes.synthetic_head(S, N, L)
     rest = np.float32(L) / np.float32(N - 1)
     of = (orc.GRID_ON if "grid" in flags_s else 0) | (orc.WIND_B if "windB" in flags_s else 0) | (orc.WIND_A if "windA" in flags_s else 0)
     p = orc.default_params(S, N, of, rest_length=rest)
     grid = orc.new_grid(p)
-    threads = orc.lib().orc_max_threads()
     L_ = orc.lib()
-    colp = np.ascontiguousarray(cols, np.float32)
-    L_.orc_step_parallel(C.byref(p), orc._f(colp), DT, 0.0, orc._f(st), grid.ctypes.data_as(orc._i64p), threads)  # warm-up
-    t0 = time.perf_counter()
-    steps = 0
-    while steps < max_steps and (time.perf_counter() - t0) < seconds:
-        L_.orc_step_parallel(C.byref(p), orc._f(colp), DT, DT * (steps + 1), orc._f(st), grid.ctypes.data_as(orc._i64p), threads)
-        steps += 1
-    el = time.perf_counter() - t0
-    return {"value": S * N * steps / el, "unit": "strand-point updates/s", "cores": threads, "kind": "port",
-            "sample": "%d strands x %d points of the same workload, %d steps, %.1f s; CPU restatement of compute.comp "
-                      "(oracle/oracle.c, OpenMP; lavapipe/Vulkan unavailable in this image)" % (S, N, steps, el),
-            "steps": steps, "seconds": el, "strands": S}
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    import rvh_b200 as rvh  # scenes only
-    S_full, N, L, flags_s, desc = WORKLOADS[args.workload]
-    # each "step" of this arm is one oracle step over a bounded sample
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
-    S = min(S_full, 131072)
-    cols = rvh.scenes.bench_colliders()
-    st = rvh.scenes.synthetic_head(S, N, L)
-    rest = np.float32(L) / np.float32(N - 1)
-    of = (orc.GRID_ON if "grid" in flags_s else 0) | (orc.WIND_B if "windB" in flags_s else 0)
-    p = orc.default_params(S, N, of, rest_length=rest)
-    grid = orc.new_grid(p)
-    threads = orc.lib().orc_max_threads()
-    L_ = orc.lib()
+    threads = L_.orc_max_threads()
     colp = np.ascontiguousarray(cols, np.float32)
 
     def one(t):
         L_.orc_step_parallel(C.byref(p), orc._f(colp), DT, t, orc._f(st), grid.ctypes.data_as(orc._i64p), threads)
 
-    for w in range(args.warmup):
+    for w in range(warmup):
         one(DT * w)
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        one(DT * (args.warmup + k))
+    for k in range(steps):
+        one(DT * (warmup + k))
     el = time.perf_counter() - t0
-    val = S * N * args.steps / el
-    sample = "%d strands x %d points per step (bounded sample of the workload), %d host threads" % (S, N, threads)
-    out = {"impl": "reference", "metric": "strand-point updates/sec", "value": val, "unit": "strand-point updates/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+    info = {"kind": "port", "cores": threads,
+            "sample": "%d strands x %d points per step, %d steps: C restatement of compute.comp (oracle/oracle.c, OpenMP over strands); "
+                      "oracle/_ref has no build of this variant (strand length %.2f / N=%d)" % (S, N, steps, L, N)}
+    return S * N * steps / el, el, info
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    S_full, N, L, flags_s, desc = WORKLOADS[args.workload]
+    steps = max(1, min(args.steps, 5))                     # each step is a bounded sample; keep the whole run to a few minutes
+    warmup = max(1, min(args.warmup, 2))
+    val, el, info = time_reference(args.workload, flags_s, steps, warmup)
+    out = {"impl": "reference", "metric": "strand-point updates/sec", "value": val, "unit": UNIT,
+           "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * el / steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": args.workload, "description": desc, "reference_arm": "CPU restatement of compute.comp (oracle/oracle.c, OpenMP): the reference is a GLSL compute shader and this image has no Vulkan/lavapipe"},
-           "cpu_baseline": {"value": val, "unit": "strand-point updates/s", "cores": threads, "kind": "port", "sample": sample},
-           "e2e": {"value": val, "unit": "strand-point updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "config": {"workload": args.workload, "description": desc, "strands_per_gpu": S_full, "points_per_strand": N, "dt": DT},
+           "cpu_baseline": dict(info, value=val, unit=UNIT),
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
     return 0
@@ -180,8 +217,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="ns_full", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spt", type=int, default=0, help="strands per thread (0 auto)")
@@ -241,7 +278,7 @@ def main():
         sim.sync()
 
     # ---- device-resident timed region -------------------------------------------------------
-    sim.step_n(max(args.warmup, 1), DT, 0.0, timed=True)
+    sim.step_n(max(args.warmup, 3), DT, 0.0, timed=True)
     sim.profile_enable(True)
     sim.profile_read()
     launches0 = sim.kernel_launches()
@@ -268,14 +305,17 @@ def main():
     else:
         peak = 6650.0; peak_src = "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
     b1, b2 = bytes_per_strand(N, grid_on)
-    k1 = prof["ftl_step"]
-    k1_ms = k1["ms"] / max(k1["launches"], 1)
+    per_kernel = {k: (v["ms"] / v["launches"] if v["launches"] else 0.0) for k, v in prof.items()}
+    dominant = max(per_kernel, key=lambda k: per_kernel[k])
+    k1_ms = per_kernel["ftl_step"]
     achieved = S * b1 / (k1_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_ftl_step", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": S * b1, "avg_launch_ms": k1_ms,
-                "per_kernel_ms": {k: (v["ms"] / v["launches"] if v["launches"] else 0.0) for k, v in prof.items()},
-                "step_bytes": S * (b1 + b2), "step_frac": (S * (b1 + b2) / (ms / args.steps * 1e-3) / 1e9) / peak}
+    roofline = {"bound": "hbm", "kernel": "k_ftl_step (integrate + collide + FTL + corrected velocity%s)" % (" + fused gather of the previous grid" if grid_on else ""),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": S * b1, "avg_launch_ms": k1_ms, "per_kernel_ms": per_kernel,
+                "longest_kernel": dominant,
+                "step_bytes": S * (b1 + b2), "step_frac": (S * (b1 + b2) / (ms / args.steps * 1e-3) / 1e9) / peak,
+                "note": "achieved = S*(48*(N-1)+12) bytes / CUDA-event time of k_ftl_step inside the timed region; step_frac = reference-shaped "
+                        "step bytes S*(84*(N-1)+12) / whole step time"}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
@@ -297,13 +337,14 @@ def main():
         el = time.perf_counter() - t0
         if dist is not None:
             t = torch.tensor([el], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); el = float(t.item())
-        e2e = {"value": world * S * N * args.e2e_steps / el, "unit": "strand-point updates/s",
+        e2e = {"value": world * S * N * args.e2e_steps / el, "unit": UNIT,
                "h2d_bytes_per_step": aos_bytes + cols.nbytes + 8, "d2h_bytes_per_step": aos_bytes,
                "steps": args.e2e_steps, "what": "rvh_step_host: upload Strand[S] AoS from pinned host memory + step + download Strand[S] AoS, every step"}
         # the reference's own per-frame contract: state stays on the GPU, only Time + Collider UBOs go in (Scene.cpp:78-87,133)
         barrier()
+        n_res = min(args.steps, 50)
         t0 = time.perf_counter()
-        for k in range(args.steps):
+        for k in range(n_res):
             sim.set_colliders(cols)
             sim.step(DT, DT * k)
             sim.draw_indirect()
@@ -311,14 +352,15 @@ def main():
         el = time.perf_counter() - t0
         if dist is not None:
             t = torch.tensor([el], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); el = float(t.item())
-        e2e_resident = {"value": world * S * N * args.steps / el, "unit": "strand-point updates/s",
-                        "h2d_bytes_per_step": cols.nbytes + 8, "d2h_bytes_per_step": 16,
+        e2e_resident = {"value": world * S * N * n_res / el, "unit": UNIT,
+                        "h2d_bytes_per_step": cols.nbytes + 8, "d2h_bytes_per_step": 16, "steps": n_res,
                         "what": "per-frame API as the reference drives it: rvh_set_colliders (UBO) + rvh_step + rvh_draw_indirect read-back; strand state resident"}
     sim.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.workload, flags_s)
+        val, el, info = time_reference(args.workload, flags_s, steps=2, warmup=1)
+        cpu = dict(info, value=val, unit=UNIT, seconds=el)
 
     if dist is not None:
         dist.barrier()
@@ -326,7 +368,7 @@ def main():
     if rank != 0:
         return 0
     out = {
-        "metric": "strand-point updates/sec", "value": value, "unit": "strand-point updates/s", "n_gpus": world,
+        "metric": "strand-point updates/sec", "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "strands_per_gpu": S, "points_per_strand": N,
