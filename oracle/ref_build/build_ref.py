@@ -96,7 +96,10 @@ def transliterate(src: str, points: int, wind: str) -> str:
     return "\n".join(fixed) + "\n"
 
 
-def run(cmd):
+def run(cmd, out=None, deps=()):
+    """Compile unless `out` is newer than every dependency."""
+    if out and os.path.exists(out) and all(os.path.exists(d) and os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return
     print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
 
@@ -118,7 +121,9 @@ def main():
     # host pieces: the reference's Strand.cpp, compiled unmodified, + Scene.h's Collider
     run([CXX] + CXXFLAGS + ["-I", os.path.join(HERE, "stubs"), "-I", src_dir, "-I", glm_inc,
                             os.path.join(HERE, "ref_host.cpp"), os.path.join(src_dir, "Strand.cpp"),
-                            "-o", os.path.join(OUT, "libref_host.so")])
+                            "-o", os.path.join(OUT, "libref_host.so")],
+        out=os.path.join(OUT, "libref_host.so"),
+        deps=[os.path.join(HERE, "ref_host.cpp"), os.path.join(src_dir, "Strand.cpp"), os.path.join(src_dir, "Scene.h"), os.path.abspath(__file__)])
 
     shader = open(os.path.join(src_dir, "shaders", "compute.comp")).read()
     for n in args.points:
@@ -128,10 +133,14 @@ def main():
             tag = "N%d%s" % (n, ("_wind" + w) if w else "")
             gen_dir = os.path.join(OUT, "gen", tag)
             os.makedirs(gen_dir, exist_ok=True)
-            with open(os.path.join(gen_dir, "compute_comp.gen.inc"), "w") as f:
-                f.write(transliterate(shader, n, w))
-            run([CXX] + CXXFLAGS + ["-I", gen_dir, "-I", glm_inc, os.path.join(HERE, "ref_compute_tu.cpp"),
-                                    "-o", os.path.join(OUT, "libref_compute_%s.so" % tag)])
+            gen = os.path.join(gen_dir, "compute_comp.gen.inc")
+            text = transliterate(shader, n, w)
+            if not os.path.exists(gen) or open(gen).read() != text:
+                with open(gen, "w") as f:
+                    f.write(text)
+            so = os.path.join(OUT, "libref_compute_%s.so" % tag)
+            run([CXX] + CXXFLAGS + ["-I", gen_dir, "-I", glm_inc, os.path.join(HERE, "ref_compute_tu.cpp"), "-o", so],
+                out=so, deps=[gen, os.path.join(HERE, "ref_compute_tu.cpp")])
     return 0
 
 
