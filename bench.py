@@ -270,6 +270,7 @@ def main():
     sim.set_colliders(cols)
     sim.upload_ptr(pinned.data_ptr(), aos_bytes)
     sim.sync()
+    exchange = sim.exchange_mode()
 
     def barrier():
         if dist is not None:
@@ -373,7 +374,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "strands_per_gpu": S, "points_per_strand": N,
                    "dt": DT, "l2": "state %.0f MB per GPU > 126 MB L2, no flush needed" % (S * N * 24 / 1e6) if S * N * 24 > 126e6 else "state %.1f MB is L2-resident (launch/latency-bound config)" % (S * N * 24 / 1e6),
-                   "parallelism": "strand-sharded x%d, NCCL int64 grid all-reduce per step" % world if world > 1 else "1 GPU",
+                   "parallelism": "strand-sharded x%d, grid exchange per step: %s" % (world, exchange) if world > 1 else "1 GPU",
                    "strands_per_thread": int(sim.cfg.strands_per_thread)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_resident,
         "gpu_launches": int(launches), "clocks": clocks,

@@ -84,11 +84,17 @@ void rvh_default_config(rvh_config* cfg, int num_strands, int num_points);
  * Scene::Scene uploads (Scene.cpp:16-20). */
 int rvh_create(rvh_ctx** out, const rvh_config* cfg);
 
-/* Multi-GPU: this context owns one contiguous shard of the strands; the voxel grid is
- * all-reduced with NCCL once per step.  nccl_unique_id is the 128-byte ncclUniqueId
- * from rvh_nccl_unique_id() on rank 0, distributed by the launcher. */
+/* Multi-GPU: this context owns one contiguous shard of the strands; only the voxel grid is
+ * exchanged, once per step.  With one process per GPU on an NVLink/NVSwitch box the exchange is
+ * ONE fused kernel per rank over CUDA-IPC peer memory (pull-reduce the rank's cell slice from all
+ * peers, finalize, push the float cells to all peers); otherwise an in-place ncclAllReduce of the
+ * int64 accumulators.  Both give bit-identical results for any rank count (integer sums).
+ * nccl_unique_id is the 128-byte ncclUniqueId from rvh_nccl_unique_id() on rank 0, distributed by
+ * the launcher; NCCL is also what carries the IPC handles at creation.  Every rank must call
+ * rvh_step (and rvh_download_grid, which all-reduces on demand) in lockstep. */
 int rvh_nccl_unique_id(void* out128);
 int rvh_create_sharded(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, const void* nccl_unique_id);
+int rvh_exchange_mode(rvh_ctx* ctx);   /* 0 = single rank, 1 = NCCL all-reduce, 2 = fused peer-memory exchange */
 
 /* Collider UBO write: Scene::Scene memcpy (Scene.cpp:10-13) and Scene::translateSphere
  * (Scene.cpp:133).  colliders = n x 192 bytes, n <= 8. */

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GRID_ON, WIND_A, WIND_B, GRID_INT32_WRAP, KEEP_CORRECTION, KEEP_ORDER = 1, 2, 4, 8, 16, 32
 
 EXPORTED_SYMBOLS = [
-    "rvh_default_config", "rvh_create", "rvh_nccl_unique_id", "rvh_create_sharded", "rvh_set_colliders",
+    "rvh_default_config", "rvh_create", "rvh_nccl_unique_id", "rvh_create_sharded", "rvh_exchange_mode", "rvh_set_colliders",
     "rvh_upload_strands_aos", "rvh_import_strands_fd", "rvh_step", "rvh_step_n", "rvh_step_host",
     "rvh_download_strands_aos", "rvh_download_grid", "rvh_draw_indirect", "rvh_step_phases",
     "rvh_profile_enable", "rvh_profile_read", "rvh_sync", "rvh_last_step_ms", "rvh_kernel_launches",
@@ -54,6 +54,7 @@ def load_library():
     L.rvh_create.argtypes = [C.POINTER(vp), C.POINTER(RvhConfig)]
     L.rvh_nccl_unique_id.argtypes = [vp]
     L.rvh_create_sharded.argtypes = [C.POINTER(vp), C.POINTER(RvhConfig), C.c_int, C.c_int, vp]
+    L.rvh_exchange_mode.argtypes = [vp]
     L.rvh_set_colliders.argtypes = [vp, vp, C.c_int]
     L.rvh_upload_strands_aos.argtypes = [vp, vp, C.c_size_t]
     L.rvh_import_strands_fd.argtypes = [vp, C.c_int, C.c_size_t]
@@ -215,6 +216,9 @@ class HairSim:
         self._check(self.L.rvh_profile_read(self.ctx, ms, n), "rvh_profile_read")
         names = ["ftl_step", "grid_gather", "grid_allreduce", "grid_clear", "grid_splat", "grid_finalize"]
         return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(names)}
+
+    def exchange_mode(self):
+        return {0: "single", 1: "nccl-allreduce", 2: "peer-memory-fused"}[int(self.L.rvh_exchange_mode(self.ctx))]
 
     def sync(self):
         self._check(self.L.rvh_sync(self.ctx), "rvh_sync")

@@ -28,6 +28,7 @@ struct NcclApi {
     int (*GetUniqueId)(NcclId*) = nullptr;
     int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
     int (*CommDestroy)(NcclComm) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool load(std::string& err) {
@@ -38,6 +39,7 @@ struct NcclApi {
         GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (int (*)(NcclComm*, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
         AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllGather");
         CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl lacks a required symbol"; return false; }
@@ -45,7 +47,7 @@ struct NcclApi {
     }
 };
 NcclApi g_nccl;
-constexpr int kNcclInt64 = 4, kNcclSum = 0;
+constexpr int kNcclInt64 = 4, kNcclSum = 0, kNcclChar = 0;
 
 enum { EV_K1 = 0, EV_K2, EV_AR, EV_CLEAR, EV_SPLAT, EV_FINALIZE, EV_COUNT };
 
@@ -75,6 +77,13 @@ struct rvh_ctx {
     // multi-GPU
     int rank = 0, nranks = 1;
     NcclComm comm = nullptr;
+    // fused peer-memory grid exchange (k_grid_exchange): peers' buffers mapped through CUDA IPC
+    bool p2p = false;
+    ExchangePeers peers;
+    unsigned* xflags = nullptr;           // [2][kMaxRanks] epochs + block counter, zero-initialised
+    void* ipc_open[3 * kMaxRanks] = {};   // mappings to close
+    unsigned epoch = 0;
+    bool grid_reduced = true;             // the int64 accumulators hold the all-rank sum (NCCL path, or 1 rank)
     // timing
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     float last_ms = 0.f;
@@ -150,6 +159,16 @@ int launch_gather(rvh_ctx* ctx) {
 // Apply a deferred gather before anything reads velocities back.
 int flush_gather(rvh_ctx* ctx) { return ctx->gather_pending ? launch_gather(ctx) : RVH_OK; }
 
+int allreduce_grid(rvh_ctx* ctx) {
+    if (ctx->grid_reduced) return RVH_OK;
+    prof_begin(ctx, EV_AR);
+    int r = g_nccl.AllReduce(ctx->grid, ctx->grid, ctx->grid_bytes / 8, kNcclInt64, kNcclSum, ctx->comm, ctx->stream);
+    prof_end(ctx);
+    if (r != 0) return fail(ctx, RVH_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    ctx->grid_reduced = true;
+    return RVH_OK;
+}
+
 // phases: bit 0 = integrate + FTL (+ splat, all-reduce), bit 1 = grid finalize + gather.
 // lazy: leave the gather to the next step's k_ftl_step (steady-state stepping); otherwise run it now.
 int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
@@ -192,17 +211,24 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
             CU(cudaGetLastError());
         }
         if (grid && ctx->nranks > 1) {
-            prof_begin(ctx, EV_AR);
-            int r = g_nccl.AllReduce(ctx->grid, ctx->grid, ctx->grid_bytes / 8, kNcclInt64, kNcclSum, ctx->comm, ctx->stream);
-            prof_end(ctx);
-            if (r != 0) return fail(ctx, RVH_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+            ctx->grid_reduced = false;
+            if (!ctx->p2p) { int r = allreduce_grid(ctx); if (r) return r; }
         }
     }
     if ((phases & 2) && grid) {
         const int cells = ctx->P.G * ctx->P.G * ctx->P.G;
-        prof_begin(ctx, EV_FINALIZE);
-        k_grid_finalize<<<(cells + 255) / 256, 256, 0, ctx->stream>>>((const long long*)ctx->grid, ctx->fgrid, cells, ctx->P.int32_wrap);
-        prof_end(ctx);
+        if (ctx->nranks > 1 && ctx->p2p && !ctx->grid_reduced) {
+            // reduce-scatter + finalize + all-gather in one kernel over NVLink peer memory (every rank calls in lockstep)
+            prof_begin(ctx, EV_AR);
+            ctx->epoch += 1;
+            const int per = (cells + ctx->nranks - 1) / ctx->nranks;
+            k_grid_exchange<<<std::min((per + 255) / 256, 148), 256, 0, ctx->stream>>>(ctx->peers, ctx->rank, ctx->nranks, cells, ctx->P.int32_wrap, ctx->epoch);
+            prof_end(ctx);
+        } else {
+            prof_begin(ctx, EV_FINALIZE);
+            k_grid_finalize<<<(cells + 255) / 256, 256, 0, ctx->stream>>>((const long long*)ctx->grid, ctx->fgrid, cells, ctx->P.int32_wrap);
+            prof_end(ctx);
+        }
         ctx->launches += 1;
         CU(cudaGetLastError());
         ctx->gather_pending = true;
@@ -216,6 +242,57 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
         CU(cudaGetLastError());
     }
     return RVH_OK;
+}
+
+// Map every peer's accumulators, float grid and flag block into this process (CUDA IPC) for k_grid_exchange.
+// All ranks take the same decision: the handles carry an "ok" byte and p2p is used only if every rank could
+// export AND open everything.  RVH_GRID_EXCHANGE=nccl forces the NCCL path.
+void setup_peer_exchange(rvh_ctx* c) {
+    struct Blob { cudaIpcMemHandle_t h[3]; int ok; int pad[15]; };
+    static_assert(sizeof(Blob) == 256, "blob layout");
+    const int R = c->nranks;
+    c->p2p = false;
+    if (R > kMaxRanks || !g_nccl.AllGather) return;
+    const char* env = std::getenv("RVH_GRID_EXCHANGE");
+    Blob mine; std::memset(&mine, 0, sizeof mine);
+    mine.ok = !(env && std::strcmp(env, "nccl") == 0);
+    if (cudaMalloc(&c->xflags, (2 * kMaxRanks + 16) * sizeof(unsigned)) != cudaSuccess) mine.ok = 0;
+    else cudaMemsetAsync(c->xflags, 0, (2 * kMaxRanks + 16) * sizeof(unsigned), c->stream);
+    if (mine.ok) {
+        if (cudaIpcGetMemHandle(&mine.h[0], c->grid) != cudaSuccess || cudaIpcGetMemHandle(&mine.h[1], c->fgrid) != cudaSuccess ||
+            cudaIpcGetMemHandle(&mine.h[2], c->xflags) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+    }
+    Blob* dsend = nullptr; Blob* drecv = nullptr;
+    std::vector<Blob> all(R);
+    bool gathered = cudaMalloc(&dsend, sizeof(Blob)) == cudaSuccess && cudaMalloc(&drecv, sizeof(Blob) * R) == cudaSuccess &&
+                    cudaMemcpyAsync(dsend, &mine, sizeof(Blob), cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+                    g_nccl.AllGather(dsend, drecv, sizeof(Blob), kNcclChar, c->comm, c->stream) == 0 &&
+                    cudaMemcpyAsync(all.data(), drecv, sizeof(Blob) * R, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+                    cudaStreamSynchronize(c->stream) == cudaSuccess;
+    int ok = gathered ? 1 : 0;
+    for (int r = 0; ok && r < R; ++r) ok = all[r].ok;
+    if (ok) {
+        for (int r = 0; r < R && ok; ++r) {
+            void* ptr[3] = { c->grid, c->fgrid, c->xflags };
+            if (r != c->rank) {
+                for (int k = 0; k < 3 && ok; ++k) {
+                    if (cudaIpcOpenMemHandle(&ptr[k], all[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+                    else c->ipc_open[3 * r + k] = ptr[k];
+                }
+            }
+            c->peers.grid[r] = (const long long*)ptr[0]; c->peers.fgrid[r] = (float4*)ptr[1]; c->peers.flags[r] = (unsigned*)ptr[2];
+        }
+    }
+    // second round: everybody must have opened everything
+    mine.ok = ok;
+    if (gathered && cudaMemcpyAsync(dsend, &mine, sizeof(Blob), cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+        g_nccl.AllGather(dsend, drecv, sizeof(Blob), kNcclChar, c->comm, c->stream) == 0 &&
+        cudaMemcpyAsync(all.data(), drecv, sizeof(Blob) * R, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+        cudaStreamSynchronize(c->stream) == cudaSuccess) {
+        for (int r = 0; ok && r < R; ++r) ok = all[r].ok;
+    } else ok = 0;
+    cudaFree(dsend); cudaFree(drecv);
+    c->p2p = ok != 0;
 }
 
 int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, const void* uid) {
@@ -287,6 +364,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
         NcclId id; std::memcpy(&id, uid, sizeof id);
         int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
         if (r != 0) { rvh_destroy(c); return fail(nullptr, RVH_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error")); }
+        setup_peer_exchange(c);           // falls back to the NCCL all-reduce when peer mapping is not possible
     }
     CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
@@ -331,6 +409,8 @@ int rvh_create_sharded(rvh_ctx** out, const rvh_config* cfg, int rank, int nrank
     if (nranks > 1 && !uid) return fail(nullptr, RVH_ERR_INVALID, "nccl_unique_id required when nranks > 1");
     return create_impl(out, cfg, rank, nranks, uid);
 }
+
+int rvh_exchange_mode(rvh_ctx* ctx) { return !ctx || ctx->nranks <= 1 ? 0 : (ctx->p2p ? 2 : 1); }
 
 int rvh_set_colliders(rvh_ctx* ctx, const void* colliders, int n) {
     if (!ctx) return RVH_ERR_INVALID;
@@ -468,6 +548,7 @@ int rvh_download_grid(rvh_ctx* ctx, void* cells, size_t bytes) {
     const size_t want = wrap ? ctx->grid_bytes / 2 : ctx->grid_bytes;
     if (!cells || bytes != want) return fail(ctx, RVH_ERR_INVALID, "grid download size mismatch");
     CU(cudaSetDevice(ctx->cfg.device));
+    if (ctx->nranks > 1) { int r = allreduce_grid(ctx); if (r) return r; }   // peer-exchange mode keeps raw per-rank accumulators (collective call)
     if (!wrap) {
         CU(cudaMemcpyAsync(cells, ctx->grid, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -525,6 +606,8 @@ void rvh_destroy(rvh_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* q : c->ipc_open) if (q) cudaIpcCloseMemHandle(q);
+    cudaFree(c->xflags);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->interop_aos) cudaFree(c->interop_aos);
     if (c->interop_mem) cudaDestroyExternalMemory(c->interop_mem);

@@ -700,6 +700,81 @@ k_grid_finalize(const long long* __restrict__ grid, float4* __restrict__ fgrid, 
     fgrid[k] = o;
 }
 
+// ---- multi-GPU: fused grid exchange over NVLink peer memory ---------------------------------------
+// Replaces  ncclAllReduce(int64 grid)  +  k_grid_finalize  by ONE kernel per rank.  Every rank's raw
+// accumulators and its float grid are mapped into all peers (CUDA IPC over NVSwitch).  Rank r owns the
+// cell slice [r*C/R, (r+1)*C/R): it LOADS that slice of every peer's int64 accumulators straight over
+// NVLink (reduce-scatter by pull), sums -- integers, so the result is the same on every rank count --,
+// converts to the gather's float4 cell exactly like k_grid_finalize, and STORES the finished cell into
+// every peer's fgrid (all-gather by push, 16 B/cell instead of the 32 B/cell an int64 all-reduce moves).
+// Per rank and step: 7/8 * 8 MiB pulled + 7/8 * 4 MiB pushed at G = 64, R = 8.
+// Two flag barriers in peer memory order it: (1) nobody reads a peer's accumulators before that peer's
+// splat kernel is finished (the peer raises its flag from THIS kernel, which is stream-ordered after its
+// splat); (2) nobody leaves the kernel before every peer has finished reading its accumulators and writing
+// its fgrid, so the next step's clear and gather are safe.  Flags carry the step epoch (monotonic).
+constexpr int kMaxRanks = 8;
+struct ExchangePeers {
+    const long long* grid[kMaxRanks];      // peers' raw int64 accumulators (read)
+    float4* fgrid[kMaxRanks];              // peers' float grids (written)
+    unsigned* flags[kMaxRanks];            // peers' flag blocks: [2][kMaxRanks] epochs + [1] local block counter
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+__global__ void __launch_bounds__(256)
+k_grid_exchange(const ExchangePeers X, int rank, int nranks, int cells, int int32_wrap, unsigned epoch) {
+    unsigned* my = X.flags[rank];
+    // ---- barrier 1: every rank's splat is complete -----------------------------------------------
+    if (blockIdx.x == 0 && threadIdx.x < nranks) st_release_sys(X.flags[threadIdx.x] + rank, epoch);
+    if (threadIdx.x < nranks) { while ((int)(ld_acquire_sys(my + threadIdx.x) - epoch) < 0) { } }
+    __syncthreads();
+    // ---- reduce my slice over all peers, finalize, broadcast ---------------------------------------
+    const int per = (cells + nranks - 1) / nranks;
+    const int lo = rank * per, hi = min(cells, lo + per);
+    for (int k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
+        // all peers' loads are issued before the first use: one NVLink round trip per cell, not one per peer
+        longlong2 a[kMaxRanks], b[kMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) {
+            if (r < nranks) {
+                const longlong2* c = reinterpret_cast<const longlong2*>(X.grid[r] + 4 * (size_t)k);
+                a[r] = c[0]; b[r] = c[1];
+            }
+        }
+        long long v0 = 0, v1 = 0, v2 = 0, dens = 0;
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) {
+            if (r < nranks) { v0 += a[r].x; v1 += a[r].y; v2 += b[r].x; dens += b[r].y; }
+        }
+        if (int32_wrap) { dens = (int)dens; v0 = (int)v0; v1 = (int)v1; v2 = (int)v2; }
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dens > 0) {
+            const float rd = __frcp_rn(__ll2float_rn(dens));
+            o.x = __ll2float_rn(v0) * rd; o.y = __ll2float_rn(v1) * rd; o.z = __ll2float_rn(v2) * rd; o.w = rd;
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) if (r < nranks) X.fgrid[r][k] = o;
+    }
+    // ---- barrier 2: all ranks done reading accumulators and writing fgrid ------------------------------
+    __threadfence_system();
+    __syncthreads();
+    unsigned* counter = my + 2 * kMaxRanks;
+    if (threadIdx.x == 0) atomicAdd(counter, 1u);
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            while (atomicAdd(counter, 0u) < gridDim.x) { }            // every block of this rank has pushed its cells
+            *counter = 0u;
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x < nranks) {
+            st_release_sys(X.flags[threadIdx.x] + kMaxRanks + rank, epoch);
+            while ((int)(ld_acquire_sys(my + kMaxRanks + threadIdx.x) - epoch) < 0) { }
+        }
+    }
+}
+
 // ---- K2: stand-alone grid gather + friction ------------------------------------------------------
 // Normally the gather of step k rides in k_ftl_step of step k+1; this kernel applies it when the state
 // is read back (download / interop pack) or a phase is requested explicitly.  One thread = one pack.

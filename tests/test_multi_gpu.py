@@ -18,7 +18,8 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, uid, S, N, L, steps, out_dir):
+def _worker(rank, world, uid, S, N, L, steps, out_dir, exchange):
+    os.environ["RVH_GRID_EXCHANGE"] = exchange
     sys.path.insert(0, ROOT)
     import rvh_b200 as rvh
     dt = float(np.float32(1.0 / 60.0))
@@ -28,6 +29,7 @@ def _worker(rank, world, uid, S, N, L, steps, out_dir):
     rest = float(np.float32(L) / np.float32(N - 1))
     cfg = rvh.default_config(hi - lo, N, flags=rvh.GRID_ON | rvh.WIND_B | rvh.KEEP_ORDER, device=rank, rest_length=rest)
     sim = rvh.HairSim(cfg, rank=rank, nranks=world, nccl_id=uid)
+    mode = sim.exchange_mode()
     sim.set_colliders(cols)
     sim.upload(st)
     for k in range(steps):
@@ -35,18 +37,22 @@ def _worker(rank, world, uid, S, N, L, steps, out_dir):
     out = sim.download()
     grid = sim.download_grid()
     sim.close()
-    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), lo=lo, hi=hi, state=out, grid=grid)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), lo=lo, hi=hi, state=out, grid=grid, mode=mode)
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("S,N,L", [(20000, 16, 0.4), (8192, 32, 2.5)])
-def test_two_gpu_sharded_equals_one_gpu(tmp_path, S, N, L):
+def test_two_gpu_sharded_equals_one_gpu(tmp_path, S, N, L, exchange):
     import torch.multiprocessing as tmp
     import rvh_b200 as rvh
     steps = 3
     uid = rvh.nccl_unique_id()
-    tmp.spawn(_worker, args=(2, uid, S, N, L, steps, str(tmp_path)), nprocs=2, join=True)
+    tmp.spawn(_worker, args=(2, uid, S, N, L, steps, str(tmp_path), exchange), nprocs=2, join=True)
     parts = [np.load(str(tmp_path / ("rank%d.npz" % r))) for r in range(2)]
+    print("grid exchange mode:", [str(p["mode"]) for p in parts])
+    if exchange == "nccl":
+        assert all(str(p["mode"]) == "nccl-allreduce" for p in parts)
     sharded = np.concatenate([p["state"] for p in parts])
     dt = float(np.float32(1.0 / 60.0))
     cols = rvh.scenes.bench_colliders()
