@@ -312,7 +312,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     rvh_ctx* c = new rvh_ctx();
     c->cfg = *cfg;
     c->S = cfg->num_strands; c->N = cfg->num_points;
-    c->S_pad = ((c->S + 127) / 128) * 128;
+    c->S_pad = ((c->S + kTileStrands - 1) / kTileStrands) * kTileStrands;
     c->rank = rank; c->nranks = nranks;
     if (const char* e = std::getenv("RVH_SPLAT_VARIANT")) c->splat_variant = std::atoi(e);
     int V = cfg->strands_per_thread;

@@ -1,10 +1,13 @@
 // rvh_kernels.cuh -- sm_100a kernels of the guide-strand physics step.
 //
 // Device-side replacement for src/shaders/compute.comp (file:line below are relative to
-// the reference tree).  Layout in HBM is point-major SoA ("planes"):
-//     planes[k][i][s]   k in {px,py,pz,vx,vy,vz}, i = point on strand, s = strand
-// so that a warp reading point i of 32*V consecutive strands issues fully coalesced
-// 32/64/128-bit loads per plane, and the root->tip chain of a strand lives in registers.
+// the reference tree).  Layout in HBM is point-major, tile-interleaved SoA ("planes"):
+//     planes[i][t][k][j]   i = point on strand (row), t = tile of 256 strands, k in {px,py,pz,vx,vy,vz},
+//                          j = strand within the tile
+// so that a warp reading point i of 32*V consecutive strands issues fully coalesced 32/64/128-bit
+// loads per plane, the six planes of a row sit at compile-time offsets (k KB) from ONE per-thread
+// pointer that advances by a uniform stride per row (no per-plane address arithmetic), and the
+// root->tip chain of a strand lives in registers.
 // The voxel grid is int64 [G^3][4] (vx,vy,vz,density), fixed point x grid_scale; integer
 // accumulation makes the result independent of atomics order and of the GPU count.
 //
@@ -23,6 +26,12 @@ namespace rvh {
 
 constexpr int kMaxEllipsoids = 7;       // colliders 1..7; collider 0 is the sphere
 constexpr int kBlock = 128;
+constexpr int kTileStrands = 256;       // strands per layout tile; S_pad is a multiple of it
+
+// element index of (row, plane k of NP, strand s) in a tiled array [N][S_pad/256][NP][256]
+__host__ __device__ __forceinline__ size_t tiled_index(int NP, int S_pad, int row, int k, int s) {
+    return (((size_t)row * (S_pad / kTileStrands) + s / kTileStrands) * NP + k) * kTileStrands + (s % kTileStrands);
+}
 
 struct Ellipsoid {
     float inv[12];   // rows 0..2 of Collider::inv      : q = inv * (p,1)     compute.comp:64-67
@@ -406,36 +415,31 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int s0 = t * V;
     if (s0 >= P.S_pad) return;
-    const size_t plane = (size_t)P.N * P.S_pad;
-    float* const ppx = planes + s0;
-    float* const ppy = ppx + plane;
-    float* const ppz = ppy + plane;
-    float* const pvx = ppz + plane;
-    float* const pvy = pvx + plane;
-    float* const pvz = pvy + plane;
+    const size_t RS = (size_t)P.S_pad * 6;                      // elements per row (all tiles, six planes)
+    constexpr int PK = kTileStrands;                              // plane stride inside a tile: compile-time offsets
+    float* const base = planes + tiled_index(6, P.S_pad, 0, 0, s0);
 
     T parx[NP], pary[NP], parz[NP];
-    load_packs<V>(ppx, parx); load_packs<V>(ppy, pary); load_packs<V>(ppz, parz);
+    load_packs<V>(base, parx); load_packs<V>(base + PK, pary); load_packs<V>(base + 2 * PK, parz);
     T nx[NP], ny[NP], nz[NP], nvx[NP], nvy[NP], nvz[NP];
-    {
-        const size_t o = P.S_pad;
-        load_packs<V>(ppx + o, nx); load_packs<V>(ppy + o, ny); load_packs<V>(ppz + o, nz);
-        load_packs<V>(pvx + o, nvx); load_packs<V>(pvy + o, nvy); load_packs<V>(pvz + o, nvz);
-    }
+    float* nextp = base + RS;                                     // row 1
+    load_packs<V>(nextp, nx); load_packs<V>(nextp + PK, ny); load_packs<V>(nextp + 2 * PK, nz);
+    load_packs<V>(nextp + 3 * PK, nvx); load_packs<V>(nextp + 4 * PK, nvy); load_packs<V>(nextp + 5 * PK, nvz);
     T lvx[NP], lvy[NP], lvz[NP];   // clamped velocity of the previous point, correction pending
 #pragma unroll
     for (int u = 0; u < NP; ++u) { lvx[u] = bc<T>(0.f); lvy[u] = bc<T>(0.f); lvz[u] = bc<T>(0.f); }
     const T minus_inv_dt = bc<T>(-P.inv_dt);
 
-    size_t oi = P.S_pad;
-    for (int i = 1; i < P.N; ++i, oi += P.S_pad) {
+    float* prevp = base;
+    for (int i = 1; i < P.N; ++i) {
+        float* const curp = nextp;
+        nextp += RS;
         T cx[NP], cy[NP], cz[NP], vx[NP], vy[NP], vz[NP];
 #pragma unroll
         for (int u = 0; u < NP; ++u) { cx[u] = nx[u]; cy[u] = ny[u]; cz[u] = nz[u]; vx[u] = nvx[u]; vy[u] = nvy[u]; vz[u] = nvz[u]; }
         if (i + 1 < P.N) {
-            const size_t o = oi + P.S_pad;
-            load_packs<V>(ppx + o, nx); load_packs<V>(ppy + o, ny); load_packs<V>(ppz + o, nz);
-            load_packs<V>(pvx + o, nvx); load_packs<V>(pvy + o, nvy); load_packs<V>(pvz + o, nvz);
+            load_packs<V>(nextp, nx); load_packs<V>(nextp + PK, ny); load_packs<V>(nextp + 2 * PK, nz);
+            load_packs<V>(nextp + 3 * PK, nvx); load_packs<V>(nextp + 4 * PK, nvy); load_packs<V>(nextp + 5 * PK, nvz);
         }
         T fvx[NP], fvy[NP], fvz[NP], odx[NP], ody[NP], odz[NP];
 #pragma unroll
@@ -448,19 +452,16 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
             fvx[u] = vfma(o.dx, minus_inv_dt, lvx[u]); fvy[u] = vfma(o.dy, minus_inv_dt, lvy[u]); fvz[u] = vfma(o.dz, minus_inv_dt, lvz[u]);
             lvx[u] = o.vx; lvy[u] = o.vy; lvz[u] = o.vz;
         }
-        store_packs<V>(ppx + oi, parx); store_packs<V>(ppy + oi, pary); store_packs<V>(ppz + oi, parz);
+        store_packs<V>(curp, parx); store_packs<V>(curp + PK, pary); store_packs<V>(curp + 2 * PK, parz);
         if (P.keep_corr) {
-            float* c0 = corr + s0 + oi;
-            store_packs<V>(c0, odx); store_packs<V>(c0 + plane, ody); store_packs<V>(c0 + 2 * plane, odz);
+            float* c0 = corr + tiled_index(3, P.S_pad, i, 0, s0);
+            store_packs<V>(c0, odx); store_packs<V>(c0 + PK, ody); store_packs<V>(c0 + 2 * PK, odz);
         }
-        if (i > 1) {
-            const size_t om = oi - P.S_pad;
-            store_packs<V>(pvx + om, fvx); store_packs<V>(pvy + om, fvy); store_packs<V>(pvz + om, fvz);
-        }
+        if (i > 1) { store_packs<V>(prevp + 3 * PK, fvx); store_packs<V>(prevp + 4 * PK, fvy); store_packs<V>(prevp + 5 * PK, fvz); }
+        prevp = curp;
     }
     // last point: no correction term (compute.comp:213 `i != NUM_CURVE_POINTS - 1`)
-    const size_t ol = (size_t)(P.N - 1) * P.S_pad;
-    store_packs<V>(pvx + ol, lvx); store_packs<V>(pvy + ol, lvy); store_packs<V>(pvz + ol, lvz);
+    store_packs<V>(prevp + 3 * PK, lvx); store_packs<V>(prevp + 4 * PK, lvy); store_packs<V>(prevp + 5 * PK, lvz);
 }
 
 // ---- K_splat: corrected velocities -> voxel grid (compute.comp:231-252) ----------------------------
@@ -518,21 +519,20 @@ k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ pla
     const bool live = s < P.S;
     if (!__any_sync(kFull, live)) return;
     const int ca = lane & 1, cb = (lane >> 1) & 1, cc = (lane >> 2) & 1, slot = lane >> 3;
-    const size_t plane = (size_t)P.N * P.S_pad;
-    const float* p0 = planes + s;
+    const size_t RS = (size_t)P.S_pad * 6;
+    const float* nextp = planes + tiled_index(6, P.S_pad, 1, 0, s);
     float nx[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) nx[k] = __ldg(p0 + k * plane + P.S_pad);
-    size_t o = P.S_pad;
+    for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
     const float2 sc2 = make_float2(P.scale, P.scale);
     for (int r = 1; r < P.N; ++r) {
         float c[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) c[k] = nx[k];
-        o += P.S_pad;
+        nextp += RS;
         if (r + 1 < P.N) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) nx[k] = __ldg(p0 + k * plane + o);
+            for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
         }
         // ---- phase A: lane = strand -------------------------------------------------------------------
         const AxisCells<float> X = axis_cells<float>(P, c[0], 0), Y = axis_cells<float>(P, c[1], 1), Z = axis_cells<float>(P, c[2], 2);
@@ -620,20 +620,19 @@ k_grid_splat_redux(const __grid_constant__ StepParams P, const float* __restrict
     const bool live = s < P.S;
     if (!__any_sync(kFull, live)) return;
     const int comp = lane & 3, ca = (lane >> 2) & 1, cb = (lane >> 3) & 1, cc = (lane >> 4) & 1;   // j = comp + 4*(a + 2b + 4c)
-    const size_t plane = (size_t)P.N * P.S_pad;
-    const float* p0 = planes + s;
+    const size_t RS = (size_t)P.S_pad * 6;
+    const float* nextp = planes + tiled_index(6, P.S_pad, 1, 0, s);
     float nx[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) nx[k] = __ldg(p0 + k * plane + P.S_pad);
-    size_t o = P.S_pad;
+    for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
     for (int r = 1; r < P.N; ++r) {
         float c[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) c[k] = nx[k];
-        o += P.S_pad;
+        nextp += RS;
         if (r + 1 < P.N) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) nx[k] = __ldg(p0 + k * plane + o);
+            for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
         }
         const AxisCells<float> X = axis_cells<float>(P, c[0], 0), Y = axis_cells<float>(P, c[1], 1), Z = axis_cells<float>(P, c[2], 2);
         const bool touches = live && (cell_ok(X.f[0], P.G) || cell_ok(X.f[0] + 1, P.G)) && (cell_ok(Y.f[0], P.G) || cell_ok(Y.f[0] + 1, P.G)) &&
@@ -780,13 +779,13 @@ k_grid_exchange(const ExchangePeers X, int rank, int nranks, int cells, int int3
 // is read back (download / interop pack) or a phase is requested explicitly.  One thread = one pack.
 __global__ void __launch_bounds__(256)
 k_grid_gather(const __grid_constant__ StepParams P, float* __restrict__ planes, const float4* __restrict__ fgrid) {
-    const size_t plane = (size_t)P.N * P.S_pad;
+    constexpr int plane = kTileStrands;
     const size_t half = (size_t)P.S_pad / 2;
     const size_t total = (size_t)(P.N - 1) * half;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
         const size_t row = k / half, s0 = 2 * (k - row * half);
         if (s0 >= (size_t)P.S) continue;
-        float* q = planes + (row + 1) * P.S_pad + s0;   // skip the root row
+        float* q = planes + tiled_index(6, P.S_pad, (int)row + 1, 0, (int)s0);   // skip the root row
         const float2 px = *reinterpret_cast<const float2*>(q), py = *reinterpret_cast<const float2*>(q + plane), pz = *reinterpret_cast<const float2*>(q + 2 * plane);
         float2 vx = *reinterpret_cast<const float2*>(q + 3 * plane), vy = *reinterpret_cast<const float2*>(q + 4 * plane), vz = *reinterpret_cast<const float2*>(q + 5 * plane);
         gather_pack<float2>(P, fgrid, px, py, pz, vx, vy, vz);
@@ -824,11 +823,10 @@ k_unpack_aos(const float4* __restrict__ aos, float* __restrict__ planes, const i
         sm[((kb + 2) * N + j) * (kTile + 1) + sl] = v.z;
     }
     __syncthreads();
-    const size_t plane = (size_t)N * S_pad;
     for (int k = threadIdx.x; k < 6 * N * kTile; k += blockDim.x) {
         const int sl = k % kTile, r = k / kTile;     // r = kk*N + j
         const int kk = r / N, j = r % N;
-        if (tile0 + sl < S_pad) planes[kk * plane + (size_t)j * S_pad + tile0 + sl] = sm[r * (kTile + 1) + sl];
+        if (tile0 + sl < S_pad) planes[tiled_index(6, S_pad, j, kk, tile0 + sl)] = sm[r * (kTile + 1) + sl];
     }
 }
 
@@ -837,15 +835,14 @@ k_pack_aos(float4* __restrict__ aos, const float* __restrict__ planes, const flo
            const int* __restrict__ perm, int S, int S_pad, int N) {
     extern __shared__ float sm[];            // [9][N][kTile+1]
     const int tile0 = blockIdx.x * kTile;
-    const size_t plane = (size_t)N * S_pad;
     const int nk = corr ? 9 : 6;
     for (int k = threadIdx.x; k < nk * N * kTile; k += blockDim.x) {
         const int sl = k % kTile, r = k / kTile;
         const int kk = r / N, j = r % N;
         float v = 0.f;
         if (tile0 + sl < S_pad)
-            v = kk < 6 ? planes[kk * plane + (size_t)j * S_pad + tile0 + sl]
-                       : corr[(kk - 6) * plane + (size_t)j * S_pad + tile0 + sl];
+            v = kk < 6 ? planes[tiled_index(6, S_pad, j, kk, tile0 + sl)]
+                       : corr[tiled_index(3, S_pad, j, kk - 6, tile0 + sl)];
         sm[r * (kTile + 1) + sl] = v;
     }
     __syncthreads();
