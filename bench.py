@@ -339,8 +339,9 @@ def main():
         if dist is not None:
             t = torch.tensor([el], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); el = float(t.item())
         e2e = {"value": world * S * N * args.e2e_steps / el, "unit": UNIT,
-               "h2d_bytes_per_step": aos_bytes + cols.nbytes + 8, "d2h_bytes_per_step": aos_bytes,
-               "steps": args.e2e_steps, "what": "rvh_step_host: upload Strand[S] AoS from pinned host memory + step + download Strand[S] AoS, every step"}
+               "h2d_bytes_per_step": S * 32 * N + cols.nbytes + 8, "d2h_bytes_per_step": S * 32 * N,
+               "steps": args.e2e_steps, "what": "rvh_step_host: upload curvePoints+curveVels of the host Strand[S] AoS (pinned), one step, download them back, "
+                                                "every step (correctionVecs are dead across steps and stay on the host)"}
         # the reference's own per-frame contract: state stays on the GPU, only Time + Collider UBOs go in (Scene.cpp:78-87,133)
         barrier()
         n_res = min(args.steps, 50)

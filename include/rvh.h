@@ -117,7 +117,9 @@ int rvh_step(rvh_ctx* ctx, float dt, float total_time);
  * timed with CUDA events on the context's stream and the call synchronises. */
 int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out);
 
-/* Host round trip in one call: upload Strand[S], one step, download Strand[S]. */
+/* Host round trip in one call: upload Strand[S], one step, download Strand[S].  Only curvePoints and
+ * curveVels cross PCIe (correctionVecs are dead on input; on output they are written only with
+ * RVH_KEEP_CORRECTION, otherwise that third of the host buffer is left untouched). */
 int rvh_step_host(rvh_ctx* ctx, void* strands_inout, size_t bytes, float dt, float total_time);
 
 /* Read-backs (synchronise).  The reference never reads these back; tests do. */

@@ -179,6 +179,12 @@ class HairSim:
     def step_host_ptr(self, ptr, nbytes, dt, total_time):
         self._check(self.L.rvh_step_host(self.ctx, C.c_void_p(ptr), nbytes, dt, total_time), "rvh_step_host")
 
+    def step_host(self, strands, dt, total_time=0.0):
+        """In place on a C-contiguous float32 [S,3,N,4] array: upload, one step, download (rvh_step_host)."""
+        assert strands.dtype == np.float32 and strands.flags["C_CONTIGUOUS"] and strands.nbytes == self.aos_bytes
+        self.step_host_ptr(strands.ctypes.data, strands.nbytes, dt, total_time)
+        return strands
+
     def step(self, dt, total_time=0.0):
         self._check(self.L.rvh_step(self.ctx, dt, total_time), "rvh_step")
 

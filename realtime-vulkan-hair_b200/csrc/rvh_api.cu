@@ -471,7 +471,10 @@ int rvh_upload_strands_aos(rvh_ctx* ctx, const void* strands, size_t bytes) {
     if (!ctx) return RVH_ERR_INVALID;
     if (!strands || bytes != ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "strands must be S*48*N bytes");
     CU(cudaSetDevice(ctx->cfg.device));
-    CU(cudaMemcpyAsync(ctx->aos_dev, strands, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // correctionVecs are dead on input (compute.comp:201 writes them before :214 reads them): only curvePoints and
+    // curveVels (the first 32*N bytes of every 48*N-byte Strand) cross PCIe
+    const size_t pitch = (size_t)48 * ctx->N, width = (size_t)32 * ctx->N;
+    CU(cudaMemcpy2DAsync(ctx->aos_dev, pitch, strands, pitch, width, ctx->S, cudaMemcpyHostToDevice, ctx->stream));
     return unpack_from_staging(ctx);
 }
 
@@ -539,7 +542,14 @@ int rvh_step_host(rvh_ctx* ctx, void* strands, size_t bytes, float dt, float tot
     if (r) return r;
     r = do_step(ctx, dt, total_time, 3, true);
     if (r) return r;
-    return rvh_download_strands_aos(ctx, strands, bytes);
+    if (ctx->corr) return rvh_download_strands_aos(ctx, strands, bytes);
+    // without RVH_KEEP_CORRECTION the correctionVecs third is not produced: bring back curvePoints + curveVels only
+    r = pack_to_staging(ctx);
+    if (r) return r;
+    const size_t pitch = (size_t)48 * ctx->N, width = (size_t)32 * ctx->N;
+    CU(cudaMemcpy2DAsync(strands, pitch, ctx->aos_dev, pitch, width, ctx->S, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RVH_OK;
 }
 
 int rvh_download_grid(rvh_ctx* ctx, void* cells, size_t bytes) {

@@ -204,6 +204,28 @@ def test_upload_download_round_trip_bit_exact():
         assert np.array_equal(bits(out), bits(st)), (S, N)
 
 
+@pytest.mark.parametrize("flags", [rvh.GRID_ON | rvh.WIND_B, rvh.GRID_ON | rvh.KEEP_CORRECTION, 0])
+def test_step_host_equals_upload_step_download(flags):
+    """rvh_step_host moves only curvePoints + curveVels over PCIe; the result must be the separate calls' result."""
+    S, N = 2500, 12
+    cols = rvh.scenes.bench_colliders()
+    st = synth(S, N, 2.5, seed_vel=17)
+    rest = float(np.float32(2.5) / np.float32(N - 1))
+    ref, _ = gpu_step(st, cols, flags, total_time=0.4, rest_length=rest)
+    cfg = rvh.default_config(S, N, flags=flags, rest_length=rest)
+    sim = rvh.HairSim(cfg)
+    sim.set_colliders(cols)
+    buf = st.copy()
+    buf[:, 2] = 123.0                                   # garbage in the dead correctionVecs third of the host buffer
+    sim.step_host(buf, DT, 0.4)
+    sim.close()
+    assert np.array_equal(bits(buf[:, 0:2]), bits(ref[:, 0:2]))
+    if flags & rvh.KEEP_CORRECTION:
+        assert np.array_equal(bits(buf[:, 2]), bits(ref[:, 2]))
+    else:
+        assert np.all(buf[:, 2] == 123.0)               # left untouched, documented in include/rvh.h
+
+
 @pytest.mark.parametrize("spt", [1, 2, 4])
 def test_strands_per_thread_variants_agree(spt):
     S, N = 3001, 24
