@@ -226,6 +226,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: every rank owns the workload's strand count; strong: the count is split over the ranks")
+    ap.add_argument("--device-init", action="store_true", help="generate the synthetic head on the GPU (rvh_init_synthetic_head) instead of uploading it")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -251,6 +253,13 @@ def main():
         nccl_id = bytes(idt.cpu().tolist())
 
     S, N, L, flags_s, desc = WORKLOADS[args.workload]
+    S_total = S * world if args.scaling == "weak" else S
+    if args.scaling == "strong":
+        lo, hi = rvh.scenes.shard_range(S_total, rank, world)
+        first_strand, S = lo, hi - lo
+    else:
+        first_strand = rank * S
+    device_init = args.device_init or S * N >= (1 << 26)
     if args.flags is not None:
         flags_s = args.flags
         desc += " [flags overridden: %s]" % flags_s
@@ -263,12 +272,17 @@ def main():
     aos_bytes = S * 48 * N
     pinned = torch.empty(aos_bytes // 4, dtype=torch.float32, pin_memory=True)
     host = pinned.numpy().reshape(S, 3, N, 4)
-    rvh.scenes.synthetic_head(S, N, L, first_strand=rank * S, colliders=cols, out=host)
+    if not device_init:
+        rvh.scenes.synthetic_head(S, N, L, first_strand=first_strand, colliders=cols, out=host)
 
     cfg = rvh.default_config(S, N, flags=flags, device=local, rest_length=rest, strands_per_thread=args.spt)
     sim = rvh.HairSim(cfg, rank=rank, nranks=world, nccl_id=nccl_id)
     sim.set_colliders(cols)
-    sim.upload_ptr(pinned.data_ptr(), aos_bytes)
+    if device_init:
+        sim.init_synthetic_head(first_strand, L, 8)
+        sim.download_ptr(pinned.data_ptr(), aos_bytes)                  # the e2e leg starts from the same state in host memory
+    else:
+        sim.upload_ptr(pinned.data_ptr(), aos_bytes)
     sim.sync()
     exchange = sim.exchange_mode()
 
@@ -297,7 +311,7 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * S * N * args.steps / (ms * 1e-3)
+    value = S_total * N * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -338,7 +352,7 @@ def main():
         el = time.perf_counter() - t0
         if dist is not None:
             t = torch.tensor([el], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); el = float(t.item())
-        e2e = {"value": world * S * N * args.e2e_steps / el, "unit": UNIT,
+        e2e = {"value": S_total * N * args.e2e_steps / el, "unit": UNIT,
                "h2d_bytes_per_step": S * 32 * N + cols.nbytes + 8, "d2h_bytes_per_step": S * 32 * N,
                "steps": args.e2e_steps, "what": "rvh_step_host: upload curvePoints+curveVels of the host Strand[S] AoS (pinned), one step, download them back, "
                                                 "every step (correctionVecs are dead across steps and stay on the host)"}
@@ -354,7 +368,7 @@ def main():
         el = time.perf_counter() - t0
         if dist is not None:
             t = torch.tensor([el], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); el = float(t.item())
-        e2e_resident = {"value": world * S * N * n_res / el, "unit": UNIT,
+        e2e_resident = {"value": S_total * N * n_res / el, "unit": UNIT,
                         "h2d_bytes_per_step": cols.nbytes + 8, "d2h_bytes_per_step": 16, "steps": n_res,
                         "what": "per-frame API as the reference drives it: rvh_set_colliders (UBO) + rvh_step + rvh_draw_indirect read-back; strand state resident"}
     sim.close()
@@ -372,8 +386,9 @@ def main():
     out = {
         "metric": "strand-point updates/sec", "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "strands_per_gpu": S, "points_per_strand": N,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "strands_per_gpu": S, "strands_total": S_total, "points_per_strand": N,
+                   "scene_init": "GPU (rvh_init_synthetic_head)" if device_init else "host (scenes.synthetic_head) + upload",
                    "dt": DT, "l2": "state %.0f MB per GPU > 126 MB L2, no flush needed" % (S * N * 24 / 1e6) if S * N * 24 > 126e6 else "state %.1f MB is L2-resident (launch/latency-bound config)" % (S * N * 24 / 1e6),
                    "parallelism": "strand-sharded x%d, grid exchange per step: %s" % (world, exchange) if world > 1 else "1 GPU",
                    "strands_per_thread": int(sim.cfg.strands_per_thread)},

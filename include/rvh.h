@@ -103,6 +103,12 @@ int rvh_set_colliders(rvh_ctx* ctx, const void* colliders, int n);
 /* Hair::Hair's strands upload (Strand.cpp:188).  bytes must be S*48*N. */
 int rvh_upload_strands_aos(rvh_ctx* ctx, const void* strands, size_t bytes);
 
+/* GPU scene init (no host traffic): the seeded synthetic head of the benchmarks -- roots on the top hemisphere
+ * of collider 1 (the head ellipsoid, main.cpp:231), counter-based splitmix64 keyed by first_strand + local
+ * index so any rank generates exactly its shard, points at rest spacing strand_length/(N-1), velocity (0,0,-1)
+ * as Strand.cpp:166.  Host twin: realtime-vulkan-hair_b200/scenes.py synthetic_head.  Needs rvh_set_colliders first. */
+int rvh_init_synthetic_head(rvh_ctx* ctx, unsigned long long first_strand, float strand_length, unsigned long long seed);
+
 /* Vulkan interop: map the exported strands VkBuffer (VK_KHR_external_memory_fd) and
  * keep it updated after every step in the reference's AoS vertex-buffer layout
  * (Renderer.cpp:2153-2161 binds it).  Needs a Vulkan device on the caller's side. */

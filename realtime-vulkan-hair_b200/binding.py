@@ -10,7 +10,7 @@ GRID_ON, WIND_A, WIND_B, GRID_INT32_WRAP, KEEP_CORRECTION, KEEP_ORDER = 1, 2, 4,
 
 EXPORTED_SYMBOLS = [
     "rvh_default_config", "rvh_create", "rvh_nccl_unique_id", "rvh_create_sharded", "rvh_exchange_mode", "rvh_set_colliders",
-    "rvh_upload_strands_aos", "rvh_import_strands_fd", "rvh_step", "rvh_step_n", "rvh_step_host",
+    "rvh_upload_strands_aos", "rvh_init_synthetic_head", "rvh_import_strands_fd", "rvh_step", "rvh_step_n", "rvh_step_host",
     "rvh_download_strands_aos", "rvh_download_grid", "rvh_draw_indirect", "rvh_step_phases",
     "rvh_profile_enable", "rvh_profile_read", "rvh_sync", "rvh_last_step_ms", "rvh_kernel_launches",
     "rvh_last_error", "rvh_destroy", "rvh_collider_build", "rvh_collider_translate", "rvh_wind_fbm",
@@ -33,7 +33,7 @@ class RvhConfig(C.Structure):
 
 
 def library_path():
-    return os.path.join(HERE, "librvh.so")
+    return os.path.join(HERE, os.environ.get("RVH_LIB", "librvh.so"))      # RVH_LIB: tuning experiments only
 
 
 _lib = None
@@ -57,6 +57,7 @@ def load_library():
     L.rvh_exchange_mode.argtypes = [vp]
     L.rvh_set_colliders.argtypes = [vp, vp, C.c_int]
     L.rvh_upload_strands_aos.argtypes = [vp, vp, C.c_size_t]
+    L.rvh_init_synthetic_head.argtypes = [vp, C.c_ulonglong, C.c_float, C.c_ulonglong]
     L.rvh_import_strands_fd.argtypes = [vp, C.c_int, C.c_size_t]
     L.rvh_step.argtypes = [vp, C.c_float, C.c_float]
     L.rvh_step_n.argtypes = [vp, C.c_int, C.c_float, C.c_float, fp]
@@ -169,6 +170,9 @@ class HairSim:
     def upload(self, strands):
         a = np.ascontiguousarray(strands, np.float32)
         self._check(self.L.rvh_upload_strands_aos(self.ctx, a.ctypes.data_as(C.c_void_p), a.nbytes), "rvh_upload_strands_aos")
+
+    def init_synthetic_head(self, first_strand=0, strand_length=2.5, seed=8):
+        self._check(self.L.rvh_init_synthetic_head(self.ctx, first_strand, strand_length, seed), "rvh_init_synthetic_head")
 
     def upload_ptr(self, ptr, nbytes):
         self._check(self.L.rvh_upload_strands_aos(self.ctx, C.c_void_p(ptr), nbytes), "rvh_upload_strands_aos")

@@ -478,6 +478,18 @@ int rvh_upload_strands_aos(rvh_ctx* ctx, const void* strands, size_t bytes) {
     return unpack_from_staging(ctx);
 }
 
+int rvh_init_synthetic_head(rvh_ctx* ctx, unsigned long long first_strand, float strand_length, unsigned long long seed) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!ctx->colliders_set || ctx->P.n_ell < 1) return fail(ctx, RVH_ERR_STATE, "rvh_init_synthetic_head needs the colliders (collider 1 = head ellipsoid) set first");
+    if (!(strand_length > 0.f)) return fail(ctx, RVH_ERR_INVALID, "strand_length must be > 0");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const float rest = strand_length / ((float)ctx->N - 1.0f);
+    k_synth_head_aos<<<(ctx->S + 255) / 256, 256, 0, ctx->stream>>>((float4*)ctx->aos_dev, ctx->S, ctx->N, first_strand, seed, rest, ctx->P.ell[0]);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return unpack_from_staging(ctx);
+}
+
 int rvh_download_strands_aos(rvh_ctx* ctx, void* strands, size_t bytes) {
     if (!ctx) return RVH_ERR_INVALID;
     if (!strands || bytes != ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "strands must be S*48*N bytes");

@@ -406,8 +406,11 @@ template <int V> __device__ __forceinline__ void store_packs(float* __restrict__
 // GATHER: the previous step's grid gather + friction (compute.comp:257-298) is applied to each velocity
 // as it is loaded -- the same positions and the same fgrid the stand-alone k_grid_gather would use -- so
 // the per-step K2 pass (re-read p,v, re-write v: 36 B/point) disappears from steady-state stepping.
+#ifndef RVH_K1_MINBLOCKS
+#define RVH_K1_MINBLOCKS 6      // <= 85 registers: 6 CTAs/SM measured fastest on B200 (5: 0.365 ms, 6: 0.357 ms, 7: 0.416 ms at 1M x 32)
+#endif
 template <int V, bool WIND, int NELL, bool GATHER>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RVH_K1_MINBLOCKS)
 k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr,
            const float4* __restrict__ fgrid) {
     using T = typename PackOf<V>::T;
@@ -479,7 +482,10 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
 // across the 4 slots and ONE warp-wide RED.64 with 32 distinct addresses (8 cells x 32 bytes).  Integer
 // sums are exact in any order, so the grid equals the shader's bit for bit, with 32x fewer atomics and
 // no shared-memory atomics or bounding boxes.
-constexpr int kSplatThreads = 128;
+#ifndef RVH_SPLAT_THREADS
+#define RVH_SPLAT_THREADS 128
+#endif
+constexpr int kSplatThreads = RVH_SPLAT_THREADS;
 constexpr float kSplatAggVmax = 60.0f;    // |c| <= 6e7 per contribution, 8 per lane, 4 lanes per corner: < 2^31
 constexpr int kStageW = 40;                // words between the a=0 and a=1 weight rows: distinct banks for LDS.64
 
@@ -862,6 +868,47 @@ k_pack_aos(float4* __restrict__ aos, const float* __restrict__ planes, const flo
         if (a == 2 && j == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);   // correctionVecs[0] is never written
         const size_t e = perm ? (size_t)perm[s] : (size_t)s;
         aos[e * q3 + q] = v;
+    }
+}
+
+// ---- GPU scene init: the seeded synthetic head (host twin: scenes.synthetic_head) ------
+// Roots on the top hemisphere of the head ellipsoid (collider 1), counter-based splitmix64 keyed by the GLOBAL
+// strand id (any rank generates exactly its shard, no host traffic), points at exact rest spacing along
+// normalize(n + 0.1*(0.05, 5, -2)), velocity (0, 0, -1).  Writes the Strand[S] AoS staging buffer, so the
+// normal unpack (+ Morton ordering) path follows.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+k_synth_head_aos(float4* __restrict__ aos, int S, int N, unsigned long long first_strand, unsigned long long seed, float rest,
+                 const __grid_constant__ Ellipsoid head) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const unsigned long long base = (seed << 32) + 2ull * (first_strand + (unsigned long long)s);
+    const float r0 = (float)(splitmix64(base) >> 40) * (1.0f / 16777216.0f);
+    const float r1 = (float)(splitmix64(base + 1ull) >> 40) * (1.0f / 16777216.0f);
+    const float uy = r0, rad = sqrtf(fmaxf(1.0f - uy * uy, 0.0f)), phi = 6.2831855f * r1;
+    const float ux = rad * cosf(phi), uz = rad * sinf(phi);
+    const float rx = head.xf[0] * ux + head.xf[1] * uy + head.xf[2] * uz + head.xf[3];
+    const float ry = head.xf[4] * ux + head.xf[5] * uy + head.xf[6] * uz + head.xf[7];
+    const float rz = head.xf[8] * ux + head.xf[9] * uy + head.xf[10] * uz + head.xf[11];
+    float nx = head.nt[0] * ux + head.nt[1] * uy + head.nt[2] * uz;
+    float ny = head.nt[3] * ux + head.nt[4] * uy + head.nt[5] * uz;
+    float nz = head.nt[6] * ux + head.nt[7] * uy + head.nt[8] * uz;
+    const float inl = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+    float dx = nx * inl + 0.1f * 0.05f, dy = ny * inl + 0.1f * 5.0f, dz = nz * inl + 0.1f * -2.0f;
+    const float idl = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= idl; dy *= idl; dz *= idl;
+    float4* cp = aos + (size_t)s * 3 * N;
+    for (int j = 0; j < N; ++j) {
+        const float t = (float)j * rest;
+        cp[j] = make_float4(rx + t * dx, ry + t * dy, rz + t * dz, 1.0f);
+        cp[N + j] = make_float4(0.0f, 0.0f, -1.0f, 0.0f);
     }
 }
 

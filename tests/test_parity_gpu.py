@@ -226,6 +226,22 @@ def test_step_host_equals_upload_step_download(flags):
         assert np.all(buf[:, 2] == 123.0)               # left untouched, documented in include/rvh.h
 
 
+def test_gpu_scene_init_matches_host_generator():
+    """rvh_init_synthetic_head (device-side splitmix64 generator) against scenes.synthetic_head (numpy), incl. a shard offset."""
+    S, N, L = 5000, 16, 0.4
+    cols = rvh.scenes.bench_colliders()
+    for first in (0, 123457):
+        cfg = rvh.default_config(S, N, flags=0, rest_length=float(np.float32(L) / np.float32(N - 1)))
+        sim = rvh.HairSim(cfg)
+        sim.set_colliders(cols)
+        sim.init_synthetic_head(first, L, 8)
+        got = sim.download()
+        sim.close()
+        want = rvh.scenes.synthetic_head(S, N, L, first_strand=first, colliders=cols)
+        assert np.abs(got[:, 0, :, :3] - want[:, 0, :, :3]).max() <= 2e-6 * 4.0      # cos/sin/sqrt differ by an ulp or two
+        assert np.array_equal(bits(got[:, 1]), bits(want[:, 1])) and np.all(got[:, 2] == 0) and np.all(got[:, 0, :, 3] == 1)
+
+
 @pytest.mark.parametrize("spt", [1, 2, 4])
 def test_strands_per_thread_variants_agree(spt):
     S, N = 3001, 24
