@@ -125,10 +125,15 @@ __device__ __forceinline__ T grid_coord(const StepParams& P, T p, int axis) {
 // The shader's [max(floor,0), min(floor+1,G-1)] cell range is exactly "cells f and f+1, each kept only
 // if it lies in [0,G-1]".  Weights clamp(1-|g-cell|,0,1): for cell f, g-f is in [0,1) so the weight is
 // 1-(g-f); for cell f+1, g-(f+1) is in [-1,0) so it is 1+(g-(f+1)); same roundings as the shader's
-// expression, no abs / clamp needed.  f is clamped to [-2, G] first (far-away / NaN points: no valid cell).
+// expression, no abs / clamp needed.  f = floor(g) comes from ONE conversion (F2I.FLOOR saturates far-away points)
+// and is clamped to [-2, G] as an integer: no valid cell outside the grid.  A NaN coordinate converts to 0, so the
+// callers exclude NaN points explicitly (nan3 below): they touch no cell, as in the oracle.
 template <class T> struct AxisCells { T w0, w1; int f[VecTraits<T>::n]; };
+__device__ __forceinline__ bool nan3(float x, float y, float z) { const float t = x + y + z; return !(t == t); }
 
-template <class T>
+// CVT_FLOOR: f from one F2I.FLOOR + integer clamp (fewer XU operations: the splat is XU-bound) instead of
+// FRND.FLOOR + float clamp + F2I (fewer registers: the gather inside k_ftl_step is register-bound).  Same f.
+template <class T, bool CVT_FLOOR>
 __device__ __forceinline__ AxisCells<T> axis_cells(const StepParams& P, T p, int axis) {
     constexpr int n = VecTraits<T>::n;
     AxisCells<T> a;
@@ -136,9 +141,15 @@ __device__ __forceinline__ AxisCells<T> axis_cells(const StepParams& P, T p, int
     T fl;
 #pragma unroll
     for (int i = 0; i < n; ++i) {
-        const float f = fminf(fmaxf(floorf(el(g, i)), -2.0f), (float)P.G);
-        setel(fl, i, f);
-        a.f[i] = (int)f;
+        if (CVT_FLOOR) {
+            const int f = max(-2, min(__float2int_rd(el(g, i)), P.G));
+            setel(fl, i, (float)f);
+            a.f[i] = f;
+        } else {
+            const float f = fminf(fmaxf(floorf(el(g, i)), -2.0f), (float)P.G);
+            setel(fl, i, f);
+            a.f[i] = (int)f;
+        }
     }
     a.w0 = vfma(vsub(g, fl), bc<T>(-1.0f), bc<T>(1.0f));
     a.w1 = vadd(vsub(g, vadd(fl, bc<T>(1.0f))), bc<T>(1.0f));
@@ -188,13 +199,14 @@ __device__ __forceinline__ void splat_point_direct(const StepParams& P, unsigned
 template <class T>
 __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* __restrict__ fgrid, T px, T py, T pz, T& vx, T& vy, T& vz) {
     constexpr int n = VecTraits<T>::n;
-    const AxisCells<T> X = axis_cells<T>(P, px, 0), Y = axis_cells<T>(P, py, 1), Z = axis_cells<T>(P, pz, 2);
+    const AxisCells<T> X = axis_cells<T, false>(P, px, 0), Y = axis_cells<T, false>(P, py, 1), Z = axis_cells<T, false>(P, pz, 2);
     float2 gxy[n]; float gz[n];
-    bool interior = true;
+    bool interior = true, isnan_[n];
 #pragma unroll
     for (int i = 0; i < n; ++i) {
         gxy[i] = make_float2(0.f, 0.f); gz[i] = 0.f;
-        interior = interior && cell_ok(X.f[i], P.G - 1) && cell_ok(Y.f[i], P.G - 1) && cell_ok(Z.f[i], P.G - 1);
+        isnan_[i] = nan3(el(px, i), el(py, i), el(pz, i));
+        interior = interior && cell_ok(X.f[i], P.G - 1) && cell_ok(Y.f[i], P.G - 1) && cell_ok(Z.f[i], P.G - 1) && !isnan_[i];
     }
     const T xy[4] = { vmul(X.w0, Y.w0), vmul(X.w1, Y.w0), vmul(X.w0, Y.w1), vmul(X.w1, Y.w1) };
     if (interior) {                                                     // all 8 corners of every point are cells
@@ -224,7 +236,7 @@ __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* _
 #pragma unroll
                 for (int ab = 0; ab < 4; ++ab) {
                     const int fx = X.f[i] + (ab & 1), fy = Y.f[i] + (ab >> 1), fz = Z.f[i] + cz;
-                    if (cell_ok(fx, P.G) && cell_ok(fy, P.G) && cell_ok(fz, P.G)) {
+                    if (!isnan_[i] && cell_ok(fx, P.G) && cell_ok(fy, P.G) && cell_ok(fz, P.G)) {
                         const float4 cell = __ldg(fgrid + (fx + (fy + fz * P.G) * P.G));
                         const float w = el(xy[ab], i) * el(cz ? Z.w1 : Z.w0, i);
                         gxy[i] = __ffma2_rn(make_float2(w, w), make_float2(cell.x, cell.y), gxy[i]);
@@ -409,8 +421,11 @@ template <int V> __device__ __forceinline__ void store_packs(float* __restrict__
 #ifndef RVH_K1_MINBLOCKS
 #define RVH_K1_MINBLOCKS 6      // <= 85 registers: 6 CTAs/SM measured fastest on B200 (5: 0.365 ms, 6: 0.357 ms, 7: 0.416 ms at 1M x 32)
 #endif
+#ifndef RVH_K1G_MINBLOCKS
+#define RVH_K1G_MINBLOCKS 5     // with the fused gather: 6 CTAs/SM spill into the loop (0.417 ms), 5: 0.362 ms, 4: 0.369 ms
+#endif
 template <int V, bool WIND, int NELL, bool GATHER>
-__global__ void __launch_bounds__(kBlock, RVH_K1_MINBLOCKS)
+__global__ void __launch_bounds__(kBlock, GATHER ? RVH_K1G_MINBLOCKS : RVH_K1_MINBLOCKS)
 k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr,
            const float4* __restrict__ fgrid) {
     using T = typename PackOf<V>::T;
@@ -541,9 +556,9 @@ k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ pla
             for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
         }
         // ---- phase A: lane = strand -------------------------------------------------------------------
-        const AxisCells<float> X = axis_cells<float>(P, c[0], 0), Y = axis_cells<float>(P, c[1], 1), Z = axis_cells<float>(P, c[2], 2);
-        const bool touches = live && (cell_ok(X.f[0], P.G) || cell_ok(X.f[0] + 1, P.G)) && (cell_ok(Y.f[0], P.G) || cell_ok(Y.f[0] + 1, P.G)) &&
-                             (cell_ok(Z.f[0], P.G) || cell_ok(Z.f[0] + 1, P.G));
+        const AxisCells<float> X = axis_cells<float, true>(P, c[0], 0), Y = axis_cells<float, true>(P, c[1], 1), Z = axis_cells<float, true>(P, c[2], 2);
+        // some corner is a cell  <=>  -1 <= f <= G-1 on every axis
+        const bool touches = live && cell_ok(X.f[0] + 1, P.G + 1) && cell_ok(Y.f[0] + 1, P.G + 1) && cell_ok(Z.f[0] + 1, P.G + 1) && !nan3(c[0], c[1], c[2]);
         const float vinf = fmaxf(fabsf(c[3]), fmaxf(fabsf(c[4]), fabsf(c[5])));
         int key = (touches && vinf <= kSplatAggVmax) ? splat_key(X.f[0], Y.f[0], Z.f[0]) : -1;
         if (touches && key == -1) {                                     // very fast (or NaN) point: 64-bit path, on its own
@@ -640,9 +655,9 @@ k_grid_splat_redux(const __grid_constant__ StepParams P, const float* __restrict
 #pragma unroll
             for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
         }
-        const AxisCells<float> X = axis_cells<float>(P, c[0], 0), Y = axis_cells<float>(P, c[1], 1), Z = axis_cells<float>(P, c[2], 2);
-        const bool touches = live && (cell_ok(X.f[0], P.G) || cell_ok(X.f[0] + 1, P.G)) && (cell_ok(Y.f[0], P.G) || cell_ok(Y.f[0] + 1, P.G)) &&
-                             (cell_ok(Z.f[0], P.G) || cell_ok(Z.f[0] + 1, P.G));
+        const AxisCells<float> X = axis_cells<float, true>(P, c[0], 0), Y = axis_cells<float, true>(P, c[1], 1), Z = axis_cells<float, true>(P, c[2], 2);
+        // some corner is a cell  <=>  -1 <= f <= G-1 on every axis
+        const bool touches = live && cell_ok(X.f[0] + 1, P.G + 1) && cell_ok(Y.f[0] + 1, P.G + 1) && cell_ok(Z.f[0] + 1, P.G + 1) && !nan3(c[0], c[1], c[2]);
         const float vinf = fmaxf(fabsf(c[3]), fmaxf(fabsf(c[4]), fabsf(c[5])));
         int key = (touches && vinf <= kSplatAggVmax) ? splat_key(X.f[0], Y.f[0], Z.f[0]) : -1;
         if (touches && key == -1) {
