@@ -53,7 +53,16 @@ enum {
     RVH_WIND_B          = 4,   /* compute.comp:152 (commented out in the reference)              */
     RVH_GRID_INT32_WRAP = 8,   /* read the grid back through its low 32 bits = reference int32   */
     RVH_KEEP_CORRECTION = 16,  /* also store correctionVecs (dead across steps; download only)   */
-    RVH_KEEP_ORDER      = 32   /* no internal Morton reordering of strands                       */
+    RVH_KEEP_ORDER      = 32,  /* no internal Morton reordering of strands                       */
+    /* North-star extensions that do NOT exist in the reference (SURVEY.md top table, section 8 f3); default off,
+     * each with its own oracle mode (oracle/oracle.c ORC_SDF_ON / ORC_REPULSION_ON). */
+    RVH_SDF_ON          = 64,  /* colliders 1..n (the analytic ellipsoids of compute.comp:170-179) are replaced by a
+                                  sampled signed-distance volume of the head (rvh_set_head_sdf / rvh_bake_head_sdf_*);
+                                  collider 0, the movable sphere, stays analytic                     */
+    RVH_REPULSION_ON    = 128, /* hair-hair repulsion: v -= repulsion * grad(rho)/rho from the same voxel grid,
+                                  applied with the friction gather (needs RVH_GRID_ON)              */
+    RVH_SDF_LDG         = 256  /* sample the SDF with plain cached loads instead of the default TMA-staged
+                                  shared-memory tiles (same results; tuning / A-B measurement)      */
 };
 
 typedef struct {              /* every field defaults to the reference constant     */
@@ -73,6 +82,7 @@ typedef struct {              /* every field defaults to the reference constant 
     float friction;           /* 0.08f                      compute.comp:296        */
     int   flags;              /* RVH_* bits; default RVH_GRID_ON                    */
     int   strands_per_thread; /* 0 = auto; 1, 2 or 4 (tuning, results identical)    */
+    float repulsion;          /* 0.02f; RVH_REPULSION_ON only (extension, not in the reference) */
 } rvh_config;
 
 /* Fill cfg with the reference constants for S strands of N points. */
@@ -108,6 +118,26 @@ int rvh_upload_strands_aos(rvh_ctx* ctx, const void* strands, size_t bytes);
  * index so any rank generates exactly its shard, points at rest spacing strand_length/(N-1), velocity (0,0,-1)
  * as Strand.cpp:166.  Host twin: realtime-vulkan-hair_b200/scenes.py synthetic_head.  Needs rvh_set_colliders first. */
 int rvh_init_synthetic_head(rvh_ctx* ctx, unsigned long long first_strand, float strand_length, unsigned long long seed);
+
+/* ---- head SDF collision (north-star extension; the reference has analytic ellipsoids only) ----------------
+ * The volume is a dense float array of signed distances at the NODES of a regular lattice, node (i,j,k) at
+ * origin + cell*(i,j,k), stored x-fastest [nz][ny][nx], negative inside.  With RVH_SDF_ON a point x whose lattice
+ * cell lies inside the volume and whose trilinearly interpolated distance d is < 0 receives the penalty
+ * penalty_k * (-d) * normalize(grad d) in place of the ellipsoid terms of compute.comp:170-179 (hit counting and
+ * the division by the number of colliders hit, compute.comp:182-184, are unchanged; the sphere stays analytic).
+ * In k_ftl_step the volume is read through TMA: per row of 256 neighbouring strands one 8x8x8-node box is staged
+ * in shared memory by cp.async.bulk.tensor.3d one row ahead of its use (RVH_SDF_LDG: plain loads instead). */
+int rvh_set_head_sdf(rvh_ctx* ctx, const float* sdf, const int dim[3], const float origin[3], float cell);
+/* GPU bake from the ellipsoid colliders 1..n currently set: signed radial distance |x - T*normalize(inv*x)|, the
+ * penetration depth compute.comp:171-172 uses, negative inside, min over the ellipsoids. */
+int rvh_bake_head_sdf_from_colliders(rvh_ctx* ctx, const int dim[3], const float origin[3], float cell);
+/* GPU bake from a triangle mesh (e.g. models/mannequin.obj, main.cpp:222): exact distance to the closest triangle,
+ * sign from the generalized winding number (robust to the open neck of the mesh).  verts = nverts x 3 floats,
+ * tris = ntris x 3 vertex indices. */
+int rvh_bake_head_sdf_from_mesh(rvh_ctx* ctx, const float* verts, int nverts, const int* tris, int ntris,
+                                const int dim[3], const float origin[3], float cell);
+int rvh_download_head_sdf(rvh_ctx* ctx, float* sdf, size_t bytes);     /* nx*ny*nz floats */
+int rvh_sdf_mode(rvh_ctx* ctx);   /* 0 = off, 1 = plain loads, 2 = TMA-staged tiles */
 
 /* Vulkan interop: map the exported strands VkBuffer (VK_KHR_external_memory_fd) and
  * keep it updated after every step in the reference's AoS vertex-buffer layout

@@ -72,6 +72,7 @@ struct rvh_ctx {
     unsigned* sort_keys = nullptr; unsigned* sort_keys_out = nullptr; int* sort_ids = nullptr;
     StepParams P;
     bool uploaded = false, colliders_set = false;
+    int splat_target_warps = 32768;       // RVH_SPLAT_WARPS env (tuning): the splat splits rows over blockIdx.y until it has this many warps
     int splat_variant = 1;                // RVH_SPLAT_VARIANT env (experiments): 1 = two-phase register accumulation (default), 0 = REDUX
     bool gather_pending = false;          // fgrid holds a finalized grid whose gather has not been applied to the velocities yet
     // multi-GPU
@@ -204,7 +205,14 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
         CU(cudaGetLastError());
         if (grid) {
             prof_begin(ctx, EV_SPLAT);
-            if (ctx->splat_variant == 1) k_grid_splat<<<ctx->S_pad / kSplatThreads, kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid);
+            if (ctx->splat_variant == 1) {
+                // enough warps to fill 148 SMs several times over: split the rows when there are few strands
+                const int warps = ctx->S_pad / 32, rows = ctx->N - 1;
+                int chunks = std::max(1, std::min(rows, (ctx->splat_target_warps + warps - 1) / warps));
+                const int rpc = (rows + chunks - 1) / chunks;
+                chunks = (rows + rpc - 1) / rpc;
+                k_grid_splat<<<dim3(ctx->S_pad / kSplatThreads, chunks), kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid, rpc);
+            }
             else k_grid_splat_redux<<<ctx->S_pad / kSplatThreads, kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid);
             prof_end(ctx);
             ctx->launches += 1;
@@ -315,6 +323,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->S_pad = ((c->S + kTileStrands - 1) / kTileStrands) * kTileStrands;
     c->rank = rank; c->nranks = nranks;
     if (const char* e = std::getenv("RVH_SPLAT_VARIANT")) c->splat_variant = std::atoi(e);
+    if (const char* e = std::getenv("RVH_SPLAT_WARPS")) c->splat_target_warps = std::max(1, std::atoi(e));
     int V = cfg->strands_per_thread;
     if (V != 1 && V != 2 && V != 4) V = c->S >= 65536 ? 2 : 1;     // measured on B200: 2 strands per thread is fastest at scale
     c->V = V;

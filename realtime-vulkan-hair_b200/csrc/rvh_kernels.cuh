@@ -531,27 +531,31 @@ __device__ __forceinline__ void splat_flush_cell(const StepParams& P, unsigned l
         global_add(grid + 4 * (size_t)(fx + (fy + fz * P.G) * P.G) + comp, (long long)mine);
 }
 
+// Rows are independent in the splat (unlike the FTL chain), so blockIdx.y splits them into chunks of
+// `rows_per_chunk`: scenes with few strands (C3: 100K x 64 = 3,125 warps walking 63 rows) still fill the machine.
 __global__ void __launch_bounds__(kSplatThreads)
-k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid) {
+k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid, int rows_per_chunk) {
     constexpr unsigned kFull = 0xffffffffu;
     __shared__ __align__(16) SplatStage stage[kSplatThreads / 32][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = blockIdx.x * kSplatThreads + threadIdx.x;            // S_pad is a multiple of 128: always in bounds
     const bool live = s < P.S;
     if (!__any_sync(kFull, live)) return;
+    const int r0 = 1 + blockIdx.y * rows_per_chunk, r1 = min(P.N, r0 + rows_per_chunk);
+    if (r0 >= r1) return;
     const int ca = lane & 1, cb = (lane >> 1) & 1, cc = (lane >> 2) & 1, slot = lane >> 3;
     const size_t RS = (size_t)P.S_pad * 6;
-    const float* nextp = planes + tiled_index(6, P.S_pad, 1, 0, s);
+    const float* nextp = planes + tiled_index(6, P.S_pad, r0, 0, s);
     float nx[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
     const float2 sc2 = make_float2(P.scale, P.scale);
-    for (int r = 1; r < P.N; ++r) {
+    for (int r = r0; r < r1; ++r) {
         float c[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) c[k] = nx[k];
         nextp += RS;
-        if (r + 1 < P.N) {
+        if (r + 1 < r1) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
         }
