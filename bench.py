@@ -41,7 +41,16 @@ WORKLOADS = {
     "c3": (100000, 64, 2.5, "grid", "C3: 100K strands x 64 points, colliders + voxel-grid friction"),
     "c4": (1000000, 16, 0.4, "grid", "C4: 1M fur strands x 16 points per GPU, voxel-grid friction"),
     "c5": (4000000, 32, 2.5, "grid+windB", "C5: 4M strands x 32 points per GPU stress (wind + colliders + grid)"),
+    # north-star extensions that the reference does not contain (own oracle modes): head SDF (TMA-staged) + repulsion
+    "c3_sdf": (100000, 64, 2.5, "grid+sdf+rep", "C3 as BASELINE.json words it: 100K strands x 64 points, head-SDF collision + voxel-grid friction + repulsion"),
+    "ns_sdf": (1 << 20, 32, 2.5, "grid+windB+sdf", "1M strands x 32 points per GPU: gravity + wind B + sphere + head SDF + voxel-grid friction"),
 }
+SDF_ORIGIN, SDF_EXTENT, SDF_CELL = (-2.0, -2.2, -1.8), (4.0, 6.2, 3.4), 0.05     # lattice over head, neck, bust and shoulders (main.cpp:229-237)
+
+
+def sdf_lattice():
+    import math
+    return [int(math.ceil(e / SDF_CELL)) + 1 for e in SDF_EXTENT], np.array(SDF_ORIGIN, np.float32), float(np.float32(SDF_CELL))
 
 
 def parse_flags(rvh, s):
@@ -52,6 +61,12 @@ def parse_flags(rvh, s):
         f |= rvh.WIND_B
     if "windA" in s:
         f |= rvh.WIND_A
+    if "sdf" in s:
+        f |= rvh.SDF_ON
+    if "sdftma" in s:
+        f |= rvh.SDF_TMA
+    if "rep" in s:
+        f |= rvh.REPULSION_ON
     return f
 
 
@@ -150,6 +165,8 @@ def time_reference(workload, flags_s, steps, warmup, strands_per_proc=8192):
     S_full, N, L, _, _ = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     tag = _ref_tag(N, flags_s) if abs(L - 2.5) < 1e-6 else None      # the shader hard-codes strand length 2.5 (compute.comp:139)
+    if "sdf" in flags_s or "rep" in flags_s:
+        tag = None                                                   # extensions do not exist in the shader: only the C port has them
     if tag is not None:
         # the shader TU keeps its buffers in globals, so each core runs its own process over its own strand range; the
         # grid is per process (as if the head were dispatched in `cores` independent pieces): same arithmetic per point
@@ -175,6 +192,10 @@ def time_reference(workload, flags_s, steps, warmup, strands_per_proc=8192):
     st = rvh.scenes.synthetic_head(S, N, L)
     rest = np.float32(L) / np.float32(N - 1)
     of = (orc.GRID_ON if "grid" in flags_s else 0) | (orc.WIND_B if "windB" in flags_s else 0) | (orc.WIND_A if "windA" in flags_s else 0)
+    of |= (orc.SDF_ON if "sdf" in flags_s else 0) | (orc.REPULSION_ON if "rep" in flags_s else 0)
+    if "sdf" in flags_s:
+        dim, origin, cell = sdf_lattice()
+        orc.set_head_sdf(orc.sdf_bake_colliders(cols, dim, origin, cell), origin, cell)
     p = orc.default_params(S, N, of, rest_length=rest)
     grid = orc.new_grid(p)
     L_ = orc.lib()
@@ -192,7 +213,7 @@ def time_reference(workload, flags_s, steps, warmup, strands_per_proc=8192):
     el = time.perf_counter() - t0
     info = {"kind": "port", "cores": threads,
             "sample": "%d strands x %d points per step, %d steps: C restatement of compute.comp (oracle/oracle.c, OpenMP over strands); "
-                      "oracle/_ref has no build of this variant (strand length %.2f / N=%d)" % (S, N, steps, L, N)}
+                      "oracle/_ref has no build of this variant (strand length %.2f / N=%d%s)" % (S, N, steps, L, N, "; extension flags" if ("sdf" in flags_s or "rep" in flags_s) else "")}
     return S * N * steps / el, el, info
 
 
@@ -278,6 +299,9 @@ def main():
     cfg = rvh.default_config(S, N, flags=flags, device=local, rest_length=rest, strands_per_thread=args.spt)
     sim = rvh.HairSim(cfg, rank=rank, nranks=world, nccl_id=nccl_id)
     sim.set_colliders(cols)
+    if flags & rvh.SDF_ON:
+        dim, origin, cell = sdf_lattice()
+        sim.bake_head_sdf_from_colliders(dim, origin, cell)     # GPU bake of the scene's own ellipsoids
     if device_init:
         sim.init_synthetic_head(first_strand, L, 8)
         sim.download_ptr(pinned.data_ptr(), aos_bytes)                  # the e2e leg starts from the same state in host memory
@@ -285,6 +309,7 @@ def main():
         sim.upload_ptr(pinned.data_ptr(), aos_bytes)
     sim.sync()
     exchange = sim.exchange_mode()
+    sdf_mode = sim.sdf_mode()
 
     def barrier():
         if dist is not None:
@@ -391,7 +416,8 @@ def main():
                    "scene_init": "GPU (rvh_init_synthetic_head)" if device_init else "host (scenes.synthetic_head) + upload",
                    "dt": DT, "l2": "state %.0f MB per GPU > 126 MB L2, no flush needed" % (S * N * 24 / 1e6) if S * N * 24 > 126e6 else "state %.1f MB is L2-resident (launch/latency-bound config)" % (S * N * 24 / 1e6),
                    "parallelism": "strand-sharded x%d, grid exchange per step: %s" % (world, exchange) if world > 1 else "1 GPU",
-                   "strands_per_thread": int(sim.cfg.strands_per_thread)},
+                   "strands_per_thread": int(sim.cfg.strands_per_thread),
+                   "head_sdf": ("%s lattice, cell %.3f, sampled through %s" % ("x".join(str(d) for d in sdf_lattice()[0]), SDF_CELL, sdf_mode)) if flags & rvh.SDF_ON else None},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_resident,
         "gpu_launches": int(launches), "clocks": clocks,
     }

@@ -59,10 +59,12 @@ enum {
     RVH_SDF_ON          = 64,  /* colliders 1..n (the analytic ellipsoids of compute.comp:170-179) are replaced by a
                                   sampled signed-distance volume of the head (rvh_set_head_sdf / rvh_bake_head_sdf_*);
                                   collider 0, the movable sphere, stays analytic                     */
-    RVH_REPULSION_ON    = 128, /* hair-hair repulsion: v -= repulsion * grad(rho)/rho from the same voxel grid,
+    RVH_REPULSION_ON    = 128, /* hair-hair repulsion: v -= repulsion * h*grad(rho)/sum(D) from the same voxel grid (each component bounded by `repulsion`),
                                   applied with the friction gather (needs RVH_GRID_ON)              */
-    RVH_SDF_LDG         = 256  /* sample the SDF with plain cached loads instead of the default TMA-staged
-                                  shared-memory tiles (same results; tuning / A-B measurement)      */
+    RVH_SDF_TMA         = 256  /* stage the SDF through TMA (warp-private 8x4x4-node shared-memory tiles, one row ahead)
+                                  instead of plain cached loads.  Bit-identical results.  Measured on B200 the staging
+                                  costs more than it saves (L1 already captures the reuse between neighbouring strands;
+                                  DESIGN.md section 8), so plain loads are the default and this is the A/B switch.  */
 };
 
 typedef struct {              /* every field defaults to the reference constant     */
@@ -82,7 +84,7 @@ typedef struct {              /* every field defaults to the reference constant 
     float friction;           /* 0.08f                      compute.comp:296        */
     int   flags;              /* RVH_* bits; default RVH_GRID_ON                    */
     int   strands_per_thread; /* 0 = auto; 1, 2 or 4 (tuning, results identical)    */
-    float repulsion;          /* 0.02f; RVH_REPULSION_ON only (extension, not in the reference) */
+    float repulsion;          /* 0.2f (velocity units); RVH_REPULSION_ON only (extension)       */
 } rvh_config;
 
 /* Fill cfg with the reference constants for S strands of N points. */
@@ -125,8 +127,8 @@ int rvh_init_synthetic_head(rvh_ctx* ctx, unsigned long long first_strand, float
  * cell lies inside the volume and whose trilinearly interpolated distance d is < 0 receives the penalty
  * penalty_k * (-d) * normalize(grad d) in place of the ellipsoid terms of compute.comp:170-179 (hit counting and
  * the division by the number of colliders hit, compute.comp:182-184, are unchanged; the sphere stays analytic).
- * In k_ftl_step the volume is read through TMA: per row of 256 neighbouring strands one 8x8x8-node box is staged
- * in shared memory by cp.async.bulk.tensor.3d one row ahead of its use (RVH_SDF_LDG: plain loads instead). */
+ * With RVH_SDF_TMA k_ftl_step reads the volume through TMA: per row of a warp's 32-64 neighbouring strands one
+ * 8x4x4-node box is staged in shared memory by cp.async.bulk.tensor.3d one row ahead of its use. */
 int rvh_set_head_sdf(rvh_ctx* ctx, const float* sdf, const int dim[3], const float origin[3], float cell);
 /* GPU bake from the ellipsoid colliders 1..n currently set: signed radial distance |x - T*normalize(inv*x)|, the
  * penetration depth compute.comp:171-172 uses, negative inside, min over the ellipsoids. */
@@ -137,7 +139,7 @@ int rvh_bake_head_sdf_from_colliders(rvh_ctx* ctx, const int dim[3], const float
 int rvh_bake_head_sdf_from_mesh(rvh_ctx* ctx, const float* verts, int nverts, const int* tris, int ntris,
                                 const int dim[3], const float origin[3], float cell);
 int rvh_download_head_sdf(rvh_ctx* ctx, float* sdf, size_t bytes);     /* nx*ny*nz floats */
-int rvh_sdf_mode(rvh_ctx* ctx);   /* 0 = off, 1 = plain loads, 2 = TMA-staged tiles */
+int rvh_sdf_mode(rvh_ctx* ctx);   /* 0 = no volume, 1 = plain loads (default), 2 = TMA-staged tiles (RVH_SDF_TMA) */
 
 /* Vulkan interop: map the exported strands VkBuffer (VK_KHR_external_memory_fd) and
  * keep it updated after every step in the reference's AoS vertex-buffer layout

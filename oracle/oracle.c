@@ -227,6 +227,7 @@ void orc_default_params(orc_params* p, int num_strands, int num_points) {
     p->friction = 0.08f;
     p->flags = ORC_GRID_ON;
     p->num_colliders = 6;
+    p->repulsion = 0.2f;
 }
 
 void orc_init_strands_reference(int S, int N, const float* roots3, const float* normals3, float* strands) {
@@ -278,6 +279,46 @@ float orc_fbm_time(float T) {
     return value;
 }
 
+/* ---- head SDF (extension; device twin: rvh_kernels.cuh sdf_cell / sdf_trilinear) ------ */
+
+static struct { const float* data; int nx, ny, nz; float origin[3], inv_cell; } g_sdf;
+
+void orc_set_head_sdf(const float* sdf, const int dim[3], const float origin[3], float cell) {
+    memset(&g_sdf, 0, sizeof g_sdf);
+    if (!sdf) return;
+    g_sdf.data = sdf; g_sdf.nx = dim[0]; g_sdf.ny = dim[1]; g_sdf.nz = dim[2];
+    for (int k = 0; k < 3; ++k) g_sdf.origin[k] = origin[k];
+    g_sdf.inv_cell = 1.0f / cell;
+}
+
+/* u = (p - origin) * inv_cell; in the volume when all 8 nodes of the cell exist; lerps are
+ * fma(t, b - a, a), x then y then z -- the same operations in the same order as the kernel. */
+int orc_sdf_sample(const float p[3], float* d_out, float grad[3]) {
+    if (!g_sdf.data) return 0;
+    const float ux = (p[0] - g_sdf.origin[0]) * g_sdf.inv_cell;
+    const float uy = (p[1] - g_sdf.origin[1]) * g_sdf.inv_cell;
+    const float uz = (p[2] - g_sdf.origin[2]) * g_sdf.inv_cell;
+    if (!(ux >= 0.f && ux < (float)(g_sdf.nx - 1) && uy >= 0.f && uy < (float)(g_sdf.ny - 1) && uz >= 0.f && uz < (float)(g_sdf.nz - 1))) return 0;
+    const int ix = (int)ux, iy = (int)uy, iz = (int)uz;
+    const float tx = ux - (float)ix, ty = uy - (float)iy, tz = uz - (float)iz;
+    const size_t sy = (size_t)g_sdf.nx, sz = (size_t)g_sdf.nx * g_sdf.ny;
+    const float* g = g_sdf.data + ix + sy * iy + sz * iz;
+    const float c0 = g[0], c1 = g[1], c2 = g[sy], c3 = g[sy + 1], c4 = g[sz], c5 = g[sz + 1], c6 = g[sz + sy], c7 = g[sz + sy + 1];
+    const float dx00 = c1 - c0, dx10 = c3 - c2, dx01 = c5 - c4, dx11 = c7 - c6;
+    const float c00 = fmaf(tx, dx00, c0), c10 = fmaf(tx, dx10, c2), c01 = fmaf(tx, dx01, c4), c11 = fmaf(tx, dx11, c6);
+    const float dy0 = c10 - c00, dy1 = c11 - c01;
+    const float e0 = fmaf(ty, dy0, c00), e1 = fmaf(ty, dy1, c01);
+    const float gz = e1 - e0;
+    *d_out = fmaf(tz, gz, e0);
+    if (grad) {
+        const float gx0 = fmaf(ty, dx10 - dx00, dx00), gx1 = fmaf(ty, dx11 - dx01, dx01);
+        grad[0] = fmaf(tz, gx1 - gx0, gx0);
+        grad[1] = fmaf(tz, dy1 - dy0, dy0);
+        grad[2] = gz;
+    }
+    return 1;
+}
+
 /* ---- the compute pass --------------------------------------------------------------- */
 
 static void integrate_strand(const orc_params* p, const float* col, float dt, float T, float fbmT, float* st) {
@@ -304,7 +345,20 @@ static void integrate_strand(const orc_params* p, const float* col, float dt, fl
 
         int hits = 0;
         v3 added = { 0.f, 0.f, 0.f };
-        for (int j = 0; j < p->num_colliders; ++j) {                            /* :158-180 */
+        const int sdf_on = (p->flags & ORC_SDF_ON) != 0;
+        if (sdf_on) {                                /* extension: the head volume stands in for colliders 1..n */
+            const float pc[3] = { cur.x, cur.y, cur.z };
+            float d, g[3];
+            if (orc_sdf_sample(pc, &d, g) && d < 0.0f) {
+                const float g2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+                if (g2 > 0.0f) {
+                    const float sc = p->penalty_k * (-d) / sqrtf(g2);
+                    added.x += sc * g[0]; added.y += sc * g[1]; added.z += sc * g[2];
+                }
+                ++hits;
+            }
+        }
+        for (int j = 0; j < (sdf_on ? (p->num_colliders > 0 ? 1 : 0) : p->num_colliders); ++j) {   /* :158-180 */
             const float* c = col + 48 * j;
             if (j == 0) {
                 v3 centre = { c[12], c[13], c[14] };
@@ -413,6 +467,8 @@ static void gather_strand(const orc_params* p, float* st, const int64_t* grid) {
     for (int i = 1; i < N; ++i) {
         cellrange c = cell_range(p, P + 4 * i);
         v3 gv = { 0.f, 0.f, 0.f };
+        float rho = 0.f, rg[3] = { 0.f, 0.f, 0.f };         /* extension: corner-density sum and h * grad(rho) */
+        const float fl[3] = { floorf(c.g[0]), floorf(c.g[1]), floorf(c.g[2]) };
         for (int a = c.lo[0]; a <= c.hi[0]; ++a)
             for (int b = c.lo[1]; b <= c.hi[1]; ++b)
                 for (int cc = c.lo[2]; cc <= c.hi[2]; ++cc) {
@@ -427,6 +483,14 @@ static void gather_strand(const orc_params* p, float* st, const int64_t* grid) {
                         float tw = xw * yw * zw;
                         float s = tw * (1.0f / (float)dens);                    /* :283 */
                         gv.x += s * (float)v0; gv.y += s * (float)v1; gv.z += s * (float)v2;
+                        if (p->flags & ORC_REPULSION_ON) {
+                            /* d/dg clamp01(1-|g-a|) = -1 for the cell at floor(g), +1 for the next one */
+                            const float D = (float)dens;
+                            rho += D;
+                            rg[0] += ((float)a  > fl[0] ? D : -D) * (yw * zw);
+                            rg[1] += ((float)b  > fl[1] ? D : -D) * (xw * zw);
+                            rg[2] += ((float)cc > fl[2] ? D : -D) * (xw * yw);
+                        }
                     }
                 }
         const float fr = p->friction, omf = 1.0f - fr;                          /* :296-297 */
@@ -434,6 +498,10 @@ static void gather_strand(const orc_params* p, float* st, const int64_t* grid) {
         V[4 * i + 1] = omf * V[4 * i + 1] + fr * gv.y;
         V[4 * i + 2] = omf * V[4 * i + 2] + fr * gv.z;
         V[4 * i + 3] = 0.0f;
+        if ((p->flags & ORC_REPULSION_ON) && rho > 0.0f) {
+            const float k = -p->repulsion / rho;            /* rho = sum of the corner densities: |rg| <= rho per component */
+            V[4 * i] += k * rg[0]; V[4 * i + 1] += k * rg[1]; V[4 * i + 2] += k * rg[2];
+        }
     }
 }
 
@@ -526,4 +594,93 @@ void orc_step_parallel(const orc_params* p, const float* col, float dt, float T,
     (void)num_threads;
     orc_step(p, col, dt, T, strands, grid);
 #endif
+}
+
+/* ---- SDF bakes (extension; device twins k_sdf_bake_colliders / k_sdf_bake_mesh) ------------ */
+
+void orc_sdf_bake_colliders(const float* col, int num_colliders, const int dim[3], const float origin[3],
+                            float cell, float* out) {
+    for (int k = 0; k < dim[2]; ++k)
+        for (int j = 0; j < dim[1]; ++j)
+            for (int i = 0; i < dim[0]; ++i) {
+                v3 p = { origin[0] + cell * (float)i, origin[1] + cell * (float)j, origin[2] + cell * (float)k };
+                float best = 1.0e9f;
+                for (int e = 1; e < num_colliders; ++e) {
+                    const float* c = col + 48 * e;
+                    v3 q = mat_mul_vec_xyz(c + 16, p, 1.0f);
+                    float q2 = q.x * q.x + q.y * q.y + q.z * q.z;
+                    v3 u = { 1.f, 0.f, 0.f };
+                    if (q2 > 0.f) { float r = 1.0f / sqrtf(q2); u.x = q.x * r; u.y = q.y * r; u.z = q.z * r; }
+                    v3 on = mat_mul_vec_xyz(c, u, 1.0f);
+                    float dist = distance3(on, p);
+                    float sd = q2 <= 1.0f ? -dist : dist;
+                    if (sd < best) best = sd;
+                }
+                out[i + (size_t)dim[0] * (j + (size_t)dim[1] * k)] = best;
+            }
+}
+
+static float tri_dist2(v3 p, v3 a, v3 b, v3 c) {       /* Ericson, Real-Time Collision Detection 5.1.5 */
+    v3 ab = sub3(b, a), ac = sub3(c, a), ap = sub3(p, a);
+    float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    v3 cp_;
+    if (d1 <= 0.f && d2 <= 0.f) { cp_.x = cp_.y = cp_.z = 0.f; }
+    else {
+        v3 bp = sub3(p, b);
+        float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+        if (d3 >= 0.f && d4 <= d3) cp_ = ab;
+        else {
+            float vc = d1 * d4 - d3 * d2;
+            if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) cp_ = scl3(d1 / (d1 - d3), ab);
+            else {
+                v3 cpv = sub3(p, c);
+                float d5 = dot3(ab, cpv), d6 = dot3(ac, cpv);
+                if (d6 >= 0.f && d5 <= d6) cp_ = ac;
+                else {
+                    float vb = d5 * d2 - d1 * d6;
+                    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) cp_ = scl3(d2 / (d2 - d6), ac);
+                    else {
+                        float va = d3 * d6 - d5 * d4;
+                        if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+                            float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+                            cp_ = add3(ab, scl3(w, sub3(ac, ab)));
+                        } else {
+                            float den = 1.0f / (va + vb + vc);
+                            cp_ = add3(scl3(vb * den, ab), scl3(vc * den, ac));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    v3 e = sub3(ap, cp_);
+    return dot3(e, e);
+}
+
+static float tri_solid_angle(v3 p, v3 A, v3 B, v3 C) {  /* Van Oosterom & Strackee 1983 */
+    v3 a = sub3(A, p), b = sub3(B, p), c = sub3(C, p);
+    float la = sqrtf(dot3(a, a)), lb = sqrtf(dot3(b, b)), lc = sqrtf(dot3(c, c));
+    float num = a.x * (b.y * c.z - b.z * c.y) + a.y * (b.z * c.x - b.x * c.z) + a.z * (b.x * c.y - b.y * c.x);
+    float den = la * lb * lc + dot3(a, b) * lc + dot3(b, c) * la + dot3(c, a) * lb;
+    return 2.0f * atan2f(num, den);
+}
+
+void orc_sdf_bake_mesh(const float* verts, const int* tris, int ntris, const int dim[3], const float origin[3],
+                       float cell, float* out) {
+    #pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k < dim[2]; ++k)
+        for (int j = 0; j < dim[1]; ++j)
+            for (int i = 0; i < dim[0]; ++i) {
+                v3 p = { origin[0] + cell * (float)i, origin[1] + cell * (float)j, origin[2] + cell * (float)k };
+                float best2 = 3.0e38f, omega = 0.f;
+                for (int t = 0; t < ntris; ++t) {
+                    const float* a = verts + 3 * (size_t)tris[3 * t], *b = verts + 3 * (size_t)tris[3 * t + 1], *c = verts + 3 * (size_t)tris[3 * t + 2];
+                    v3 A = { a[0], a[1], a[2] }, B = { b[0], b[1], b[2] }, C = { c[0], c[1], c[2] };
+                    float d2 = tri_dist2(p, A, B, C);
+                    if (d2 < best2) best2 = d2;
+                    omega += tri_solid_angle(p, A, B, C);
+                }
+                float d = sqrtf(best2);
+                out[i + (size_t)dim[0] * (j + (size_t)dim[1] * k)] = fabsf(omega) > 6.2831855f ? -d : d;   /* |winding| > 1/2 */
+            }
 }

@@ -45,7 +45,11 @@ enum {
     ORC_GRID_ON         = 1,   /* phases P2 splat + P3 gather (compute.comp:211-298)  */
     ORC_WIND_A          = 2,   /* compute.comp:151 (commented out in the reference)   */
     ORC_WIND_B          = 4,   /* compute.comp:152 (commented out in the reference)   */
-    ORC_GRID_INT32_WRAP = 8    /* emulate the reference's int32 GridCell (Scene.h:42) */
+    ORC_GRID_INT32_WRAP = 8,   /* emulate the reference's int32 GridCell (Scene.h:42) */
+    /* Extensions named by the north star that the reference does NOT contain; these modes are the
+     * definition the CUDA path is checked against (include/rvh.h RVH_SDF_ON / RVH_REPULSION_ON). */
+    ORC_SDF_ON          = 64,  /* colliders 1..n replaced by a sampled head SDF (orc_set_head_sdf) */
+    ORC_REPULSION_ON    = 128  /* v -= repulsion * h*grad(rho)/sum(D) with the friction gather   */
 };
 
 typedef struct {
@@ -64,6 +68,7 @@ typedef struct {
     float friction;         /* 0.08f                             compute.comp:296     */
     int   flags;
     int   num_colliders;    /* 6; index 0 is the sphere          compute.comp:8,160   */
+    float repulsion;        /* 0.2f; ORC_REPULSION_ON only (extension)                */
 } orc_params;
 
 /* Fill every field with the reference constant for (S, N). */
@@ -96,6 +101,18 @@ void orc_phase_gather(const orc_params* p, float* strands, const int64_t* grid);
 void orc_step_parallel(const orc_params* p, const float* colliders48, float dt,
                        float total_time, float* strands, int64_t* grid, int num_threads);
 int  orc_max_threads(void);
+
+/* ---- extensions (not in the reference) ------------------------------------------------ */
+/* Head SDF: node values [nz][ny][nx], x fastest, node (i,j,k) at origin + cell*(i,j,k), negative
+ * inside.  The pointer is kept (not copied) until the next call; NULL clears it. */
+void orc_set_head_sdf(const float* sdf, const int dim[3], const float origin[3], float cell);
+/* Trilinear sample exactly as the step uses it; returns 0 when the point's cell is outside. */
+int  orc_sdf_sample(const float p[3], float* d, float grad[3]);
+/* Bakes (CPU twins of k_sdf_bake_colliders / k_sdf_bake_mesh): */
+void orc_sdf_bake_colliders(const float* colliders48, int num_colliders, const int dim[3],
+                            const float origin[3], float cell, float* out);
+void orc_sdf_bake_mesh(const float* verts, const int* tris, int ntris, const int dim[3],
+                       const float origin[3], float cell, float* out);
 
 /* Hair::Hair initial state (Strand.cpp:157-175) from follicle roots + normals. */
 void orc_init_strands_reference(int S, int N, const float* roots3, const float* normals3,

@@ -6,7 +6,7 @@ CUDA library.  There is no CPU fallback: importing works without a GPU (so symbo
 checked), creating a simulation does not.
 """
 from .binding import (  # noqa: F401
-    GRID_ON, WIND_A, WIND_B, GRID_INT32_WRAP, KEEP_CORRECTION, KEEP_ORDER,
+    GRID_ON, WIND_A, WIND_B, GRID_INT32_WRAP, KEEP_CORRECTION, KEEP_ORDER, SDF_ON, REPULSION_ON, SDF_TMA,
     RvhConfig, RvhError, HairSim, load_library, library_path, default_config,
     collider_build, collider_translate, wind_fbm, nccl_unique_id, EXPORTED_SYMBOLS,
 )

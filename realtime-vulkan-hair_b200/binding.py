@@ -7,6 +7,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 GRID_ON, WIND_A, WIND_B, GRID_INT32_WRAP, KEEP_CORRECTION, KEEP_ORDER = 1, 2, 4, 8, 16, 32
+SDF_ON, REPULSION_ON, SDF_TMA = 64, 128, 256      # north-star extensions, not in the reference (include/rvh.h)
 
 EXPORTED_SYMBOLS = [
     "rvh_default_config", "rvh_create", "rvh_nccl_unique_id", "rvh_create_sharded", "rvh_exchange_mode", "rvh_set_colliders",
@@ -14,7 +15,8 @@ EXPORTED_SYMBOLS = [
     "rvh_download_strands_aos", "rvh_download_grid", "rvh_draw_indirect", "rvh_step_phases",
     "rvh_profile_enable", "rvh_profile_read", "rvh_sync", "rvh_last_step_ms", "rvh_kernel_launches",
     "rvh_last_error", "rvh_destroy", "rvh_collider_build", "rvh_collider_translate", "rvh_wind_fbm",
-    "rvh_abi_version",
+    "rvh_abi_version", "rvh_set_head_sdf", "rvh_bake_head_sdf_from_colliders", "rvh_bake_head_sdf_from_mesh",
+    "rvh_download_head_sdf", "rvh_sdf_mode",
 ]
 
 
@@ -28,7 +30,7 @@ class RvhConfig(C.Structure):
         ("gravity_y", C.c_float), ("damping", C.c_float), ("vmax", C.c_float), ("penalty_k", C.c_float),
         ("sphere_radius", C.c_float), ("grid_dim", C.c_int), ("grid_extent", C.c_float),
         ("grid_origin", C.c_float * 3), ("grid_scale", C.c_float), ("friction", C.c_float), ("flags", C.c_int),
-        ("strands_per_thread", C.c_int),
+        ("strands_per_thread", C.c_int), ("repulsion", C.c_float),
     ]
 
 
@@ -83,13 +85,21 @@ def load_library():
     L.rvh_collider_translate.restype = None
     L.rvh_wind_fbm.argtypes = [C.c_float]
     L.rvh_wind_fbm.restype = C.c_float
+    ip = C.POINTER(C.c_int)
+    L.rvh_set_head_sdf.argtypes = [vp, fp, ip, fp, C.c_float]
+    L.rvh_bake_head_sdf_from_colliders.argtypes = [vp, ip, fp, C.c_float]
+    L.rvh_bake_head_sdf_from_mesh.argtypes = [vp, fp, C.c_int, ip, C.c_int, ip, fp, C.c_float]
+    L.rvh_download_head_sdf.argtypes = [vp, fp, C.c_size_t]
+    L.rvh_sdf_mode.argtypes = [vp]
     _lib = L
     return L
 
 
-def default_config(num_strands, num_points, flags=GRID_ON, device=0, rest_length=None, strands_per_thread=0):
+def default_config(num_strands, num_points, flags=GRID_ON, device=0, rest_length=None, strands_per_thread=0, repulsion=None):
     cfg = RvhConfig()
     load_library().rvh_default_config(C.byref(cfg), num_strands, num_points)
+    if repulsion is not None:
+        cfg.repulsion = repulsion
     cfg.flags = flags
     cfg.device = device
     cfg.strands_per_thread = strands_per_thread
@@ -226,6 +236,42 @@ class HairSim:
         self._check(self.L.rvh_profile_read(self.ctx, ms, n), "rvh_profile_read")
         names = ["ftl_step", "grid_gather", "grid_allreduce", "grid_clear", "grid_splat", "grid_finalize"]
         return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(names)}
+
+    # ---- head SDF (extension) ----
+    @staticmethod
+    def _dim_origin(dim, origin):
+        d = np.asarray(dim, np.int32).copy()
+        o = np.asarray(origin, np.float32).copy()
+        return d, o, d.ctypes.data_as(C.POINTER(C.c_int)), _fptr(o)
+
+    def set_head_sdf(self, vol, origin, cell):
+        """vol: float32 [nz][ny][nx] signed distances at the lattice nodes (negative inside)."""
+        v = np.ascontiguousarray(vol, np.float32)
+        d, o, dp, op = self._dim_origin([v.shape[2], v.shape[1], v.shape[0]], origin)
+        self._check(self.L.rvh_set_head_sdf(self.ctx, _fptr(v), dp, op, cell), "rvh_set_head_sdf")
+        self._sdf_dim = tuple(int(x) for x in d)
+
+    def bake_head_sdf_from_colliders(self, dim, origin, cell):
+        d, o, dp, op = self._dim_origin(dim, origin)
+        self._check(self.L.rvh_bake_head_sdf_from_colliders(self.ctx, dp, op, cell), "rvh_bake_head_sdf_from_colliders")
+        self._sdf_dim = tuple(int(x) for x in d)
+
+    def bake_head_sdf_from_mesh(self, verts, tris, dim, origin, cell):
+        v = np.ascontiguousarray(verts, np.float32)
+        t = np.ascontiguousarray(tris, np.int32)
+        d, o, dp, op = self._dim_origin(dim, origin)
+        self._check(self.L.rvh_bake_head_sdf_from_mesh(self.ctx, _fptr(v), v.shape[0], t.ctypes.data_as(C.POINTER(C.c_int)), t.shape[0], dp, op, cell),
+                    "rvh_bake_head_sdf_from_mesh")
+        self._sdf_dim = tuple(int(x) for x in d)
+
+    def download_head_sdf(self):
+        nx, ny, nz = self._sdf_dim
+        out = np.empty((nz, ny, nx), np.float32)
+        self._check(self.L.rvh_download_head_sdf(self.ctx, _fptr(out), out.nbytes), "rvh_download_head_sdf")
+        return out
+
+    def sdf_mode(self):
+        return {0: "off", 1: "ldg", 2: "tma"}[int(self.L.rvh_sdf_mode(self.ctx))]
 
     def exchange_mode(self):
         return {0: "single", 1: "nccl-allreduce", 2: "peer-memory-fused"}[int(self.L.rvh_exchange_mode(self.ctx))]

@@ -75,6 +75,13 @@ struct rvh_ctx {
     int splat_target_warps = 32768;       // RVH_SPLAT_WARPS env (tuning): the splat splits rows over blockIdx.y until it has this many warps
     int splat_variant = 1;                // RVH_SPLAT_VARIANT env (experiments): 1 = two-phase register accumulation (default), 0 = REDUX
     bool gather_pending = false;          // fgrid holds a finalized grid whose gather has not been applied to the velocities yet
+    // head SDF (extension)
+    float* sdf_dev = nullptr;             // [nz][ny][nxp] node values
+    int sdf_dim[3] = { 0, 0, 0 }, sdf_nxp = 0;
+    int sdf_mode = 0;                     // 0 = no volume, 1 = plain loads, 2 = TMA-staged tiles
+    CUtensorMap sdf_map;                  // 3-D tiled map of the volume, box 8x4x4 nodes (zeroed when unused)
+    float* bake_tris = nullptr;
+    float sdf_cell = 0.f;
     // multi-GPU
     int rank = 0, nranks = 1;
     NcclComm comm = nullptr;
@@ -134,12 +141,22 @@ void prof_collect(rvh_ctx* c) {   // caller has synchronised the stream
 }
 
 template <int V, bool WIND, int NELL>
-void launch_k1(rvh_ctx* c, bool gather) {
-    if (gather) k_ftl_step<V, WIND, NELL, true><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid);
-    else        k_ftl_step<V, WIND, NELL, false><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid);
+void launch_k1(rvh_ctx* c, int gather) {
+    // gather: 0 = none pending, 1 = friction, 2 = friction + repulsion (extension: V <= 2 only, see create_impl)
+    if (gather == 2) {
+        if constexpr (V <= 2) k_ftl_step<V, WIND, NELL, 2><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map);
+    } else if (gather == 1) k_ftl_step<V, WIND, NELL, 1><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map);
+    else                    k_ftl_step<V, WIND, NELL, 0><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map);
 }
 template <int V>
-void launch_k1_v(rvh_ctx* c, bool wind, bool gather) {
+void launch_k1_v(rvh_ctx* c, bool wind, int gather) {
+    if (c->cfg.flags & RVH_SDF_ON) {      // head SDF in place of the ellipsoids: -3 = TMA-staged tiles, -2 = plain loads
+        if constexpr (V <= 2) {
+            if (c->sdf_mode == 2) { if (wind) launch_k1<V, true, -3>(c, gather); else launch_k1<V, false, -3>(c, gather); }
+            else                  { if (wind) launch_k1<V, true, -2>(c, gather); else launch_k1<V, false, -2>(c, gather); }
+        }
+        return;
+    }
     const bool five = c->P.n_ell == 5;     // the reference scene's collider count gets the unrolled kernel
     if (wind) { if (five) launch_k1<V, true, 5>(c, gather); else launch_k1<V, true, -1>(c, gather); }
     else      { if (five) launch_k1<V, false, 5>(c, gather); else launch_k1<V, false, -1>(c, gather); }
@@ -149,7 +166,8 @@ int launch_gather(rvh_ctx* ctx) {
     prof_begin(ctx, EV_K2);
     const size_t total = (size_t)(ctx->N - 1) * (ctx->S_pad / 2);
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 64);
-    k_grid_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->fgrid);
+    if (ctx->cfg.flags & RVH_REPULSION_ON) k_grid_gather<true><<<blocks, 256, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->fgrid);
+    else                                   k_grid_gather<false><<<blocks, 256, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->fgrid);
     prof_end(ctx);
     ctx->launches += 1;
     CU(cudaGetLastError());
@@ -186,6 +204,8 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
         P.wind_T3 = (float)std::fmod((double)(total_time * 3.0f), 6.283185307179586);   // sin(5z + 3T): keep the argument bounded
         P.wind_amp = (P.wind_mode == 2) ? 7.0f * wind_fbm(total_time) : 10.0f;
     }
+    if ((flags & RVH_SDF_ON) && !ctx->sdf_dev)
+        return fail(ctx, RVH_ERR_STATE, "RVH_SDF_ON but no head SDF: call rvh_set_head_sdf or rvh_bake_head_sdf_* first");
     if (phases & 1) {
         if (grid) {
             prof_begin(ctx, EV_CLEAR);
@@ -193,7 +213,7 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
             prof_end(ctx);
         }
         prof_begin(ctx, EV_K1);
-        const bool fused_gather = ctx->gather_pending;
+        const int fused_gather = ctx->gather_pending ? ((flags & RVH_REPULSION_ON) ? 2 : 1) : 0;
         switch (ctx->V) {
             case 4: launch_k1_v<4>(ctx, wind, fused_gather); break;
             case 2: launch_k1_v<2>(ctx, wind, fused_gather); break;
@@ -310,6 +330,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     if (cfg->num_strands < 1 || cfg->num_points < 2) return fail(nullptr, RVH_ERR_INVALID, "need num_strands >= 1 and num_points >= 2");
     if (cfg->grid_dim < 2 || cfg->grid_dim > 1024) return fail(nullptr, RVH_ERR_INVALID, "grid_dim out of range");
     if ((size_t)cfg->num_strands * cfg->num_points > ((size_t)1 << 31)) return fail(nullptr, RVH_ERR_INVALID, "S*N too large for one context");
+    if ((cfg->flags & RVH_REPULSION_ON) && !(cfg->flags & RVH_GRID_ON)) return fail(nullptr, RVH_ERR_INVALID, "RVH_REPULSION_ON needs RVH_GRID_ON (it reads the same voxel grid)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -326,7 +347,9 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     if (const char* e = std::getenv("RVH_SPLAT_WARPS")) c->splat_target_warps = std::max(1, std::atoi(e));
     int V = cfg->strands_per_thread;
     if (V != 1 && V != 2 && V != 4) V = c->S >= 65536 ? 2 : 1;     // measured on B200: 2 strands per thread is fastest at scale
+    if ((cfg->flags & (RVH_SDF_ON | RVH_REPULSION_ON)) && V == 4) V = 2;   // the extension kernels exist for 1 and 2 strands per thread
     c->V = V;
+    std::memset(&c->sdf_map, 0, sizeof c->sdf_map);
     ctx = c;
 #define CUC(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e2_); rvh_destroy(c); return fail(nullptr, RVH_ERR_CUDA, m_); } } while (0)
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -364,6 +387,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     }
     for (int k = 0; k < 3; ++k) P.origin[k] = cfg->grid_origin[k];
     P.scale = cfg->grid_scale; P.friction = cfg->friction;
+    P.repulsion = cfg->repulsion; P.inv_h = 1.0f / P.h;
     P.int32_wrap = (cfg->flags & RVH_GRID_INT32_WRAP) ? 1 : 0;
     P.keep_corr = c->corr ? 1 : 0;
 
@@ -385,7 +409,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
 
 extern "C" {
 
-int rvh_abi_version(void) { return 1; }
+int rvh_abi_version(void) { return 2; }   // 2: rvh_config.repulsion, head SDF entry points
 
 void rvh_default_config(rvh_config* cfg, int num_strands, int num_points) {
     std::memset(cfg, 0, sizeof *cfg);
@@ -399,6 +423,7 @@ void rvh_default_config(rvh_config* cfg, int num_strands, int num_points) {
     cfg->grid_scale = 1000000.0f; cfg->friction = 0.08f;
     cfg->flags = RVH_GRID_ON;
     cfg->strands_per_thread = 0;
+    cfg->repulsion = 0.2f;
 }
 
 int rvh_create(rvh_ctx** out, const rvh_config* cfg) { return create_impl(out, cfg, 0, 1, nullptr); }
@@ -510,6 +535,107 @@ int rvh_download_strands_aos(rvh_ctx* ctx, void* strands, size_t bytes) {
     CU(cudaStreamSynchronize(ctx->stream));
     return RVH_OK;
 }
+
+// ---- head SDF (extension) ---------------------------------------------------------------------------
+static int sdf_alloc(rvh_ctx* ctx, const int dim[3], const float origin[3], float cell) {
+    if (!dim || !origin) return fail(ctx, RVH_ERR_INVALID, "null argument");
+    if (dim[0] < 2 || dim[1] < 2 || dim[2] < 2 || (size_t)dim[0] * dim[1] * dim[2] > ((size_t)1 << 30)) return fail(ctx, RVH_ERR_INVALID, "SDF dims must be >= 2 per axis and <= 2^30 nodes");
+    if (!(cell > 0.f)) return fail(ctx, RVH_ERR_INVALID, "SDF cell must be > 0");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->sdf_dev); ctx->sdf_dev = nullptr; ctx->sdf_mode = 0;
+    const int nxp = (dim[0] + 3) & ~3;                               // 16-byte rows (TMA stride rule)
+    CU(cudaMalloc(&ctx->sdf_dev, (size_t)nxp * dim[1] * dim[2] * sizeof(float)));
+    for (int k = 0; k < 3; ++k) { ctx->sdf_dim[k] = dim[k]; ctx->P.sdf.origin[k] = origin[k]; }
+    ctx->sdf_nxp = nxp;
+    SdfVolume& V = ctx->P.sdf;
+    V.data = ctx->sdf_dev; V.nx = dim[0]; V.ny = dim[1]; V.nz = dim[2]; V.nxp = nxp; V.inv_cell = 1.0f / cell;
+    ctx->sdf_cell = cell;
+    // TMA descriptor: rank-3 tiled map over the TRUE extents (padding columns are outside the tensor), box 8x4x4 nodes
+    ctx->sdf_mode = 1;
+    std::memset(&ctx->sdf_map, 0, sizeof ctx->sdf_map);
+    const char* env = std::getenv("RVH_SDF_TMA");
+    const bool want_tma = ((ctx->cfg.flags & RVH_SDF_TMA) || (env && std::atoi(env))) && ctx->V <= 2 && dim[0] >= kSdfBoxX && dim[1] >= kSdfBoxY && dim[2] >= kSdfBoxZ;
+    if (want_tma) {
+        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn && q == cudaDriverEntryPointSuccess) {
+            const cuuint64_t gdim[3] = { (cuuint64_t)dim[0], (cuuint64_t)dim[1], (cuuint64_t)dim[2] };
+            const cuuint64_t gstr[2] = { (cuuint64_t)nxp * 4, (cuuint64_t)nxp * dim[1] * 4 };
+            const cuuint32_t box[3] = { kSdfBoxX, kSdfBoxY, kSdfBoxZ }, estr[3] = { 1, 1, 1 };
+            CUresult r = ((EncodeTiled)fn)(&ctx->sdf_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ctx->sdf_dev, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) ctx->sdf_mode = 2;
+            else std::memset(&ctx->sdf_map, 0, sizeof ctx->sdf_map);
+        } else cudaGetLastError();
+    }
+    return RVH_OK;
+}
+
+int rvh_set_head_sdf(rvh_ctx* ctx, const float* sdf, const int dim[3], const float origin[3], float cell) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!sdf) return fail(ctx, RVH_ERR_INVALID, "null SDF");
+    int r = sdf_alloc(ctx, dim, origin, cell);
+    if (r) return r;
+    const int nx = dim[0], nxp = ctx->sdf_nxp;
+    std::vector<float> padded((size_t)nxp * dim[1] * dim[2], kSdfFar);
+    for (size_t row = 0; row < (size_t)dim[1] * dim[2]; ++row) std::memcpy(&padded[row * nxp], sdf + row * nx, sizeof(float) * nx);
+    CU(cudaMemcpy(ctx->sdf_dev, padded.data(), padded.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return RVH_OK;
+}
+
+int rvh_bake_head_sdf_from_colliders(rvh_ctx* ctx, const int dim[3], const float origin[3], float cell) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!ctx->colliders_set || ctx->P.n_ell < 1) return fail(ctx, RVH_ERR_STATE, "rvh_bake_head_sdf_from_colliders needs ellipsoid colliders (rvh_set_colliders, n >= 2)");
+    int r = sdf_alloc(ctx, dim, origin, cell);
+    if (r) return r;
+    const size_t total = (size_t)ctx->sdf_nxp * dim[1] * dim[2];
+    k_sdf_bake_colliders<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->P, ctx->sdf_dev, dim[0], dim[1], dim[2], ctx->sdf_nxp, origin[0], origin[1], origin[2], cell);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RVH_OK;
+}
+
+int rvh_bake_head_sdf_from_mesh(rvh_ctx* ctx, const float* verts, int nverts, const int* tris, int ntris,
+                                const int dim[3], const float origin[3], float cell) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!verts || !tris || nverts < 3 || ntris < 1) return fail(ctx, RVH_ERR_INVALID, "mesh needs >= 3 vertices and >= 1 triangle");
+    std::vector<float> t9((size_t)ntris * 9);
+    for (int t = 0; t < ntris; ++t)
+        for (int k = 0; k < 3; ++k) {
+            const int v = tris[3 * t + k];
+            if (v < 0 || v >= nverts) return fail(ctx, RVH_ERR_INVALID, "triangle index out of range");
+            for (int a = 0; a < 3; ++a) t9[(size_t)t * 9 + 3 * k + a] = verts[3 * (size_t)v + a];
+        }
+    int r = sdf_alloc(ctx, dim, origin, cell);
+    if (r) return r;
+    cudaFree(ctx->bake_tris); ctx->bake_tris = nullptr;
+    CU(cudaMalloc(&ctx->bake_tris, t9.size() * sizeof(float)));
+    CU(cudaMemcpy(ctx->bake_tris, t9.data(), t9.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t total = (size_t)ctx->sdf_nxp * dim[1] * dim[2];
+    k_sdf_bake_mesh<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->sdf_dev, dim[0], dim[1], dim[2], ctx->sdf_nxp, origin[0], origin[1], origin[2], cell, ctx->bake_tris, ntris);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RVH_OK;
+}
+
+int rvh_download_head_sdf(rvh_ctx* ctx, float* sdf, size_t bytes) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!ctx->sdf_dev) return fail(ctx, RVH_ERR_STATE, "no head SDF set");
+    const size_t nx = ctx->sdf_dim[0], rows = (size_t)ctx->sdf_dim[1] * ctx->sdf_dim[2];
+    if (!sdf || bytes != nx * rows * sizeof(float)) return fail(ctx, RVH_ERR_INVALID, "SDF download must be nx*ny*nz floats");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy2D(sdf, nx * sizeof(float), ctx->sdf_dev, (size_t)ctx->sdf_nxp * sizeof(float), nx * sizeof(float), rows, cudaMemcpyDeviceToHost));
+    return RVH_OK;
+}
+
+int rvh_sdf_mode(rvh_ctx* ctx) { return ctx ? ctx->sdf_mode : 0; }
+
 
 int rvh_import_strands_fd(rvh_ctx* ctx, int fd, size_t bytes) {
     if (!ctx) return RVH_ERR_INVALID;
@@ -642,6 +768,7 @@ void rvh_destroy(rvh_ctx* c) {
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->interop_aos) cudaFree(c->interop_aos);
     if (c->interop_mem) cudaDestroyExternalMemory(c->interop_mem);
+    cudaFree(c->sdf_dev); cudaFree(c->bake_tris);
     cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->fgrid); cudaFree(c->perm); cudaFree(c->aos_dev);
     cudaFree(c->sort_tmp); cudaFree(c->sort_keys); cudaFree(c->sort_keys_out); cudaFree(c->sort_ids);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);

@@ -20,6 +20,7 @@
 //   k_grid_gather                   stand-alone gather, only when state is read back before the next step
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>            // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdint.h>
 
 namespace rvh {
@@ -39,6 +40,14 @@ struct Ellipsoid {
     float nt[9];     // upper 3x3 of Collider::invTrans : n = nt * q          compute.comp:70-73
 };
 
+// Head SDF (north-star extension, include/rvh.h): node values [nz][ny][nxp], x fastest, nxp = nx rounded up to 4
+// floats so that the rows satisfy TMA's 16-byte stride rule.
+struct SdfVolume {
+    const float* data;
+    int nx, ny, nz, nxp;
+    float origin[3], inv_cell;
+};
+
 struct StepParams {
     int S, S_pad, N;
     float rest, gravity_y, damping, vmax, vmax2, penalty_k;
@@ -52,6 +61,8 @@ struct StepParams {
     int wind_mode;                          // 0 off, 1 = variant A (:151), 2 = variant B (:152)
     float wind_s2T, wind_T3, wind_amp;      // 2*sin(2T); 3T mod 2pi; 10 (A) or 7*fbm(sinT,cosT) (B)
     int int32_wrap, keep_corr;
+    SdfVolume sdf;                          // RVH_SDF_ON
+    float repulsion, inv_h;                 // RVH_REPULSION_ON: v -= repulsion * h*grad(rho)/sum(D) (gather_pack); inv_h = 1/h
 };
 
 // ---- wind trigonometry ---------------------------------------------------------------------------
@@ -193,12 +204,20 @@ __device__ __forceinline__ void splat_point_direct(const StepParams& P, unsigned
 }
 
 // ---- P3 gather + friction of one pack: compute.comp:259-297 ---------------------------------------
-// fgrid[cell] = (vx, vy, vz) / density as floats (zero where density <= 0), prepared once per step by
+// fgrid[cell] = (vx, vy, vz) / density as floats, .w = float(density) (all zero where density <= 0), prepared once per step by
 // k_grid_finalize, so a corner costs one LDG.128 and three FMAs (one FFMA2 + one FFMA).  Floating point:
 // agrees with the shader's  w * (1/d) * v  to a few ulp (tolerance-checked, not bit-compared).
-template <class T>
+// REP (extension, include/rvh.h RVH_REPULSION_ON): with rho = sum_c w_c D_c the trilinear density over the 8 corner cells
+// (D_c = fgrid.w = float(density), 0 where density <= 0) and grad rho its analytic gradient (d w/d g = -1 for cell f, +1 for
+// cell f+1, times 1/h), the velocity also gets  v -= repulsion * h * grad(rho) / sum_c D_c  after the friction blend: a push
+// down the density gradient whose every component is bounded by `repulsion` whatever the strand count (|h grad rho| <= sum D).
+// Oracle twin: oracle.c gather_strand.
+template <class T, bool REP>
 __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* __restrict__ fgrid, T px, T py, T pz, T& vx, T& vy, T& vz) {
     constexpr int n = VecTraits<T>::n;
+    float rho[n], rgx[n], rgy[n], rgz[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) { rho[i] = 0.f; rgx[i] = 0.f; rgy[i] = 0.f; rgz[i] = 0.f; }
     const AxisCells<T> X = axis_cells<T, false>(P, px, 0), Y = axis_cells<T, false>(P, py, 1), Z = axis_cells<T, false>(P, pz, 2);
     float2 gxy[n]; float gz[n];
     bool interior = true, isnan_[n];
@@ -226,6 +245,13 @@ __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* _
                     const float w = el(tw, i);
                     gxy[i] = __ffma2_rn(make_float2(w, w), make_float2(cell.x, cell.y), gxy[i]);
                     gz[i] = fmaf(w, cell.z, gz[i]);
+                    if (REP) {
+                        const float D = cell.w, wz = el(cz ? Z.w1 : Z.w0, i);
+                        rho[i] += D;
+                        rgx[i] = fmaf((ab & 1) ? D : -D, el((ab >> 1) ? Y.w1 : Y.w0, i) * wz, rgx[i]);
+                        rgy[i] = fmaf((ab >> 1) ? D : -D, el((ab & 1) ? X.w1 : X.w0, i) * wz, rgy[i]);
+                        rgz[i] = fmaf(cz ? D : -D, el(xy[ab], i), rgz[i]);
+                    }
                 }
             }
     } else {
@@ -241,6 +267,13 @@ __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* _
                         const float w = el(xy[ab], i) * el(cz ? Z.w1 : Z.w0, i);
                         gxy[i] = __ffma2_rn(make_float2(w, w), make_float2(cell.x, cell.y), gxy[i]);
                         gz[i] = fmaf(w, cell.z, gz[i]);
+                        if (REP) {
+                            const float D = cell.w, wz = el(cz ? Z.w1 : Z.w0, i);
+                            rho[i] += D;
+                            rgx[i] = fmaf((ab & 1) ? D : -D, el((ab >> 1) ? Y.w1 : Y.w0, i) * wz, rgx[i]);
+                            rgy[i] = fmaf((ab >> 1) ? D : -D, el((ab & 1) ? X.w1 : X.w0, i) * wz, rgy[i]);
+                            rgz[i] = fmaf(cz ? D : -D, el(xy[ab], i), rgz[i]);
+                        }
                     }
                 }
     }
@@ -249,6 +282,99 @@ __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* _
     for (int i = 0; i < n; ++i) { setel(gx, i, gxy[i].x); setel(gy, i, gxy[i].y); setel(gzz, i, gz[i]); }
     const T fr = bc<T>(P.friction), omf = bc<T>(1.0f - P.friction);     // :296-297
     vx = vfma(fr, gx, vmul(omf, vx)); vy = vfma(fr, gy, vmul(omf, vy)); vz = vfma(fr, gzz, vmul(omf, vz));
+    if (REP) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            if (rho[i] > 0.f) {
+                const float k = -P.repulsion / rho[i];                  // rho = sum of the corner densities
+                setel(vx, i, fmaf(k, rgx[i], el(vx, i))); setel(vy, i, fmaf(k, rgy[i], el(vy, i))); setel(vz, i, fmaf(k, rgz[i], el(vz, i)));
+            }
+        }
+    }
+}
+
+// ---- head SDF sampling (north-star extension; oracle twin: oracle.c sdf_cell / sdf_trilinear) -------------
+// Lattice coordinate u = (p - origin) * inv_cell per axis; the point is "in the volume" when all 8 nodes of its
+// cell exist.  d = trilinear interpolation, x then y then z, each lerp = fma(t, b - a, a): the same operations in
+// the same order as the oracle, so the inside/outside decision (d < 0) is bit-identical on both sides.
+// One TMA-staged tile = 8 x 4 x 4 nodes (512 B), private to a WARP (see k_ftl_step).  TMA needs the box's global start
+// address 16-byte aligned, i.e. the x coordinate a multiple of 4 floats (an unaligned x coordinate faults as "illegal
+// instruction": scripts/probes/tma_probe.cu), so the tile's x origin is the row's minimum cell rounded DOWN to 4 and the
+// box is 8 wide: reach >= 4 x 3 x 3 cells from the minimum cell of the warp's 32*V neighbouring strands.
+constexpr int kSdfBoxX = 8, kSdfBoxY = 4, kSdfBoxZ = 4;
+constexpr int kSdfTileFloats = kSdfBoxX * kSdfBoxY * kSdfBoxZ;
+constexpr int kSdfTileBytes = kSdfTileFloats * 4;
+struct SdfTile {                              // the staged tile as the consumer threads see it
+    const float* data;                        // shared memory [4][4][8], x fastest; nullptr = no tile (plain loads)
+    int ox, oy, oz;                           // node index of tile element (0,0,0)
+};
+
+__device__ __forceinline__ bool sdf_cell(const SdfVolume& V, float x, float y, float z, int& ix, int& iy, int& iz,
+                                         float& tx, float& ty, float& tz) {
+    const float ux = __fmul_rn(__fsub_rn(x, V.origin[0]), V.inv_cell);
+    const float uy = __fmul_rn(__fsub_rn(y, V.origin[1]), V.inv_cell);
+    const float uz = __fmul_rn(__fsub_rn(z, V.origin[2]), V.inv_cell);
+    const bool in = ux >= 0.f && ux < (float)(V.nx - 1) && uy >= 0.f && uy < (float)(V.ny - 1) && uz >= 0.f && uz < (float)(V.nz - 1);
+    ix = (int)ux; iy = (int)uy; iz = (int)uz;                          // u >= 0: truncation = floor (unused when !in)
+    tx = __fsub_rn(ux, (float)ix); ty = __fsub_rn(uy, (float)iy); tz = __fsub_rn(uz, (float)iz);
+    return in;
+}
+
+__device__ __forceinline__ void sdf_corners(const SdfVolume& V, const SdfTile& T, int ix, int iy, int iz, float (&c)[8]) {
+    if (T.data) {
+        const int lx = ix - T.ox, ly = iy - T.oy, lz = iz - T.oz;
+        if ((unsigned)lx < (unsigned)(kSdfBoxX - 1) && (unsigned)ly < (unsigned)(kSdfBoxY - 1) && (unsigned)lz < (unsigned)(kSdfBoxZ - 1)) {
+            constexpr int sy = kSdfBoxX, sz = kSdfBoxX * kSdfBoxY;
+            const float* t = T.data + lx + sy * ly + sz * lz;
+            c[0] = t[0]; c[1] = t[1]; c[2] = t[sy]; c[3] = t[sy + 1];
+            c[4] = t[sz]; c[5] = t[sz + 1]; c[6] = t[sz + sy]; c[7] = t[sz + sy + 1];
+            return;
+        }
+    }
+    const size_t sy = (size_t)V.nxp, sz = (size_t)V.nxp * V.ny;        // the row's bounding box left the tile: plain loads
+    const float* g = V.data + ix + sy * iy + sz * iz;
+    c[0] = __ldg(g); c[1] = __ldg(g + 1); c[2] = __ldg(g + sy); c[3] = __ldg(g + sy + 1);
+    c[4] = __ldg(g + sz); c[5] = __ldg(g + sz + 1); c[6] = __ldg(g + sz + sy); c[7] = __ldg(g + sz + sy + 1);
+}
+
+__device__ __forceinline__ float sdf_trilinear(const float (&c)[8], float tx, float ty, float tz) {
+    const float c00 = fmaf(tx, __fsub_rn(c[1], c[0]), c[0]), c10 = fmaf(tx, __fsub_rn(c[3], c[2]), c[2]);
+    const float c01 = fmaf(tx, __fsub_rn(c[5], c[4]), c[4]), c11 = fmaf(tx, __fsub_rn(c[7], c[6]), c[6]);
+    const float c0 = fmaf(ty, __fsub_rn(c10, c00), c00), c1 = fmaf(ty, __fsub_rn(c11, c01), c01);
+    return fmaf(tz, __fsub_rn(c1, c0), c0);
+}
+
+// is the point inside the head?  (the test half; the force half is in collision_force)
+__device__ __forceinline__ bool sdf_inside(const SdfVolume& V, const SdfTile& T, float x, float y, float z) {
+    int ix, iy, iz; float tx, ty, tz;
+    if (!sdf_cell(V, x, y, z, ix, iy, iz, tx, ty, tz)) return false;
+    float c[8];
+    sdf_corners(V, T, ix, iy, iz, c);
+    return sdf_trilinear(c, tx, ty, tz) < 0.f;
+}
+
+// ---- TMA / mbarrier primitives for the staged SDF tiles (sm_100a PTX) ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a tile that never lands is a bug, and a trap is better than a hung GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    for (unsigned spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // ---- P1 for one point (or one pack of two): compute.comp:144-201 --------------------------------
@@ -264,7 +390,9 @@ __device__ __forceinline__ T ellipsoid_q(const Ellipsoid& E, T cx, T cy, T cz, T
 }
 
 // Penalty force of the colliders in `hit` on ONE point (the divergent part; compute.comp:160-184).
-__device__ __forceinline__ void collision_force(const StepParams& P, unsigned hit, float cx, float cy, float cz,
+// SDF: bit 1 of `hit` is the head volume (penalty_k * (-d) * normalize(grad d), include/rvh.h) instead of ellipsoid 1.
+template <bool SDF>
+__device__ __forceinline__ void collision_force(const StepParams& P, const SdfTile& tile, unsigned hit, float cx, float cy, float cz,
                                                 float& ox, float& oy, float& oz) {
     float ax = 0.f, ay = 0.f, az = 0.f;
     if (hit & 1u) {                                                     // sphere, :160-169
@@ -274,7 +402,26 @@ __device__ __forceinline__ void collision_force(const StepParams& P, unsigned hi
         const float s = P.penalty_k * (P.sphere_r - d2 * rinv) * rinv;
         ax = s * dx; ay = s * dy; az = s * dz;
     }
-    unsigned m = hit >> 1;
+    if (SDF && (hit & 2u)) {
+        int ix, iy, iz; float tx, ty, tz;
+        sdf_cell(P.sdf, cx, cy, cz, ix, iy, iz, tx, ty, tz);
+        float c[8];
+        sdf_corners(P.sdf, tile, ix, iy, iz, c);
+        const float dx00 = __fsub_rn(c[1], c[0]), dx10 = __fsub_rn(c[3], c[2]), dx01 = __fsub_rn(c[5], c[4]), dx11 = __fsub_rn(c[7], c[6]);
+        const float c00 = fmaf(tx, dx00, c[0]), c10 = fmaf(tx, dx10, c[2]), c01 = fmaf(tx, dx01, c[4]), c11 = fmaf(tx, dx11, c[6]);
+        const float dy0 = __fsub_rn(c10, c00), dy1 = __fsub_rn(c11, c01);
+        const float c0 = fmaf(ty, dy0, c00), c1 = fmaf(ty, dy1, c01);
+        const float gz = __fsub_rn(c1, c0);
+        const float d = fmaf(tz, gz, c0);                              // the same d sdf_inside found < 0
+        const float gx0 = fmaf(ty, dx10 - dx00, dx00), gx1 = fmaf(ty, dx11 - dx01, dx01);
+        const float gx = fmaf(tz, gx1 - gx0, gx0), gy = fmaf(tz, dy1 - dy0, dy0);   // gradient of the trilinear interpolant (x inv_cell, cancels)
+        const float g2 = fmaf(gx, gx, fmaf(gy, gy, gz * gz));
+        if (g2 > 0.f) {
+            const float sc = P.penalty_k * (-d) * rsqrt_fast(g2);
+            ax = fmaf(sc, gx, ax); ay = fmaf(sc, gy, ay); az = fmaf(sc, gz, az);
+        }
+    }
+    unsigned m = SDF ? 0u : hit >> 1;
     while (m) {                                                         // ellipsoids, :170-179
         const int j = __ffs(m) - 1;
         m &= m - 1;
@@ -299,9 +446,10 @@ __device__ __forceinline__ void collision_force(const StepParams& P, unsigned hi
     ox = ax * ih; oy = ay * ih; oz = az * ih;
 }
 
-// NELL >= 0: number of ellipsoids known at compile time; NELL < 0: run-time count.
+// NELL >= 0: number of ellipsoids known at compile time; NELL == -1: run-time count; NELL <= -2: the head SDF replaces
+// the ellipsoids (-2 plain loads, -3 TMA-staged tile in `tile`).
 template <class T, bool WIND, int NELL>
-__device__ __forceinline__ PointOut<T> point_update(const StepParams& P, T cx, T cy, T cz, T vx, T vy, T vz,
+__device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const SdfTile& tile, T cx, T cy, T cz, T vx, T vy, T vz,
                                                     T parx, T pary, T parz) {
     constexpr int n = VecTraits<T>::n;
     T fx = bc<T>(0.0f), fy = bc<T>(P.gravity_y), fz = bc<T>(0.0f);       // :150
@@ -343,13 +491,16 @@ __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, T cx, T
 #pragma unroll
             for (int i = 0; i < n; ++i) if (el(q2, i) <= 1.0f) hit[i] |= 2u << j;                       // :66
         }
-    } else {
+    } else if (NELL == -1) {
         for (int j = 0; j < P.n_ell; ++j) {
             T qx, qy, qz;
             const T q2 = ellipsoid_q<T>(P.ell[j], cx, cy, cz, qx, qy, qz);
 #pragma unroll
             for (int i = 0; i < n; ++i) if (el(q2, i) <= 1.0f) hit[i] |= 2u << j;
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < n; ++i) if (sdf_inside(P.sdf, tile, el(cx, i), el(cy, i), el(cz, i))) hit[i] |= 2u;
     }
     unsigned any_hit = 0;
 #pragma unroll
@@ -360,7 +511,7 @@ __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, T cx, T
         for (int i = 0; i < n; ++i) {
             if (hit[i]) {
                 float ox, oy, oz;
-                collision_force(P, hit[i], el(cx, i), el(cy, i), el(cz, i), ox, oy, oz);
+                collision_force<(NELL <= -2)>(P, tile, hit[i], el(cx, i), el(cy, i), el(cz, i), ox, oy, oz);
                 setel(ax, i, ox); setel(ay, i, oy); setel(az, i, oz);
             }
         }
@@ -418,21 +569,68 @@ template <int V> __device__ __forceinline__ void store_packs(float* __restrict__
 // GATHER: the previous step's grid gather + friction (compute.comp:257-298) is applied to each velocity
 // as it is loaded -- the same positions and the same fgrid the stand-alone k_grid_gather would use -- so
 // the per-step K2 pass (re-read p,v, re-write v: 36 B/point) disappears from steady-state stepping.
+// GATHER = 2 adds the repulsion extension to it.
+//
+// NELL == -3 (head SDF through TMA): a warp owns 32*V Morton-neighbouring strands, whose row-i points sit within a
+// few SDF cells of each other.  One row AHEAD of its use the warp reduces the minimum lattice cell of the row's points
+// (3 REDUX.MIN), lane 0 arms the warp's mbarrier and issues ONE cp.async.bulk.tensor.3d for the 8x4x4-node box at that
+// corner (512 B, zero-filled outside the volume) into the warp's double-buffered tile; a row later the lanes wait on the
+// mbarrier's phase and read their 8 corners with LDS.  Points whose cell falls outside the box take plain loads.
+// Everything is warp-private (tile, mbarrier, box origin in registers): no __syncthreads, the warps of a CTA keep
+// drifting apart as in the other variants.  Positions are prefetched TWO rows ahead (velocities one), so that the box
+// corner is known a full row before the tile is needed.
 #ifndef RVH_K1_MINBLOCKS
 #define RVH_K1_MINBLOCKS 6      // <= 85 registers: 6 CTAs/SM measured fastest on B200 (5: 0.365 ms, 6: 0.357 ms, 7: 0.416 ms at 1M x 32)
 #endif
 #ifndef RVH_K1G_MINBLOCKS
 #define RVH_K1G_MINBLOCKS 5     // with the fused gather: 6 CTAs/SM spill into the loop (0.417 ms), 5: 0.362 ms, 4: 0.369 ms
 #endif
-template <int V, bool WIND, int NELL, bool GATHER>
-__global__ void __launch_bounds__(kBlock, GATHER ? RVH_K1G_MINBLOCKS : RVH_K1_MINBLOCKS)
+#ifndef RVH_K1X_MINBLOCKS
+#define RVH_K1X_MINBLOCKS 4     // extension variants (SDF and/or repulsion): more live state
+#endif
+struct __align__(128) SdfStageSmem {
+    float tile[kBlock / 32][2][kSdfTileFloats];
+    unsigned long long bar[kBlock / 32][2];
+};
+
+// Whole warp: reduce the minimum in-volume lattice cell of `row`'s points, lane 0 stages the warp's tile for that row.
+// Returns the tile origin (node index) in o0..o2, identical in all lanes.
+template <class T, int NP>
+__device__ __forceinline__ void sdf_stage_row(const StepParams& P, const CUtensorMap* tmap, SdfStageSmem& sm, int row,
+                                              const T (&px)[NP], const T (&py)[NP], const T (&pz)[NP], int& o0, int& o1, int& o2) {
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr int kNone = 0x7fffffff;
+    int m0 = kNone, m1 = kNone, m2 = kNone;
+#pragma unroll
+    for (int u = 0; u < NP; ++u)
+#pragma unroll
+        for (int e = 0; e < VecTraits<T>::n; ++e) {
+            int ix, iy, iz; float tx, ty, tz;
+            if (sdf_cell(P.sdf, el(px[u], e), el(py[u], e), el(pz[u], e), ix, iy, iz, tx, ty, tz)) { m0 = min(m0, ix); m1 = min(m1, iy); m2 = min(m2, iz); }
+        }
+    m0 = __reduce_min_sync(kFull, m0); m1 = __reduce_min_sync(kFull, m1); m2 = __reduce_min_sync(kFull, m2);   // also: every lane is done with the tile this buffer held two rows ago
+    o0 = m0 == kNone ? 0 : (m0 & ~3);      // 16-byte aligned box start (see kSdfBoxX)
+    o1 = m1 == kNone ? 0 : m1;
+    o2 = m2 == kNone ? 0 : m2;
+    if ((threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5, par = row & 1;
+        mbar_expect_tx(&sm.bar[w][par], kSdfTileBytes);
+        tma_load_3d(sm.tile[w][par], tmap, &sm.bar[w][par], o0, o1, o2);
+    }
+}
+
+template <int V, bool WIND, int NELL, int GATHER>
+__global__ void __launch_bounds__(kBlock, (NELL <= -2 || GATHER == 2) ? RVH_K1X_MINBLOCKS : (GATHER ? RVH_K1G_MINBLOCKS : RVH_K1_MINBLOCKS))
 k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr,
-           const float4* __restrict__ fgrid) {
+           const float4* __restrict__ fgrid, const __grid_constant__ CUtensorMap sdf_map) {
     using T = typename PackOf<V>::T;
     constexpr int NP = PackOf<V>::n;
+    constexpr bool TMA = NELL == -3;
+    __shared__ __align__(128) unsigned char sdf_raw[TMA ? sizeof(SdfStageSmem) : 16];
+    SdfStageSmem& sm = *reinterpret_cast<SdfStageSmem*>(sdf_raw);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int s0 = t * V;
-    if (s0 >= P.S_pad) return;
+    if (!TMA && s0 >= P.S_pad) return;                            // TMA variant: S_pad is a multiple of kBlock*V (V <= 2), no partial CTA
     const size_t RS = (size_t)P.S_pad * 6;                      // elements per row (all tiles, six planes)
     constexpr int PK = kTileStrands;                              // plane stride inside a tile: compile-time offsets
     float* const base = planes + tiled_index(6, P.S_pad, 0, 0, s0);
@@ -443,6 +641,19 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
     float* nextp = base + RS;                                     // row 1
     load_packs<V>(nextp, nx); load_packs<V>(nextp + PK, ny); load_packs<V>(nextp + 2 * PK, nz);
     load_packs<V>(nextp + 3 * PK, nvx); load_packs<V>(nextp + 4 * PK, nvy); load_packs<V>(nextp + 5 * PK, nvz);
+    T n2x[NP], n2y[NP], n2z[NP];                                  // TMA only: positions two rows ahead
+    unsigned phase = 0;                                           // TMA only: mbarrier phase bit per buffer
+    int bx = 0, by = 0, bz = 0;                                   // TMA only: origin of the tile of the row being consumed
+    const int wid = threadIdx.x >> 5;
+    if constexpr (TMA) {
+        if (P.N > 2) { load_packs<V>(nextp + RS, n2x); load_packs<V>(nextp + RS + PK, n2y); load_packs<V>(nextp + RS + 2 * PK, n2z); }
+        if ((threadIdx.x & 31) == 0) {
+            mbar_init(&sm.bar[wid][0], 1); mbar_init(&sm.bar[wid][1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        sdf_stage_row<T, NP>(P, &sdf_map, sm, 1, nx, ny, nz, bx, by, bz);
+    }
     T lvx[NP], lvy[NP], lvz[NP];   // clamped velocity of the previous point, correction pending
 #pragma unroll
     for (int u = 0; u < NP; ++u) { lvx[u] = bc<T>(0.f); lvy[u] = bc<T>(0.f); lvz[u] = bc<T>(0.f); }
@@ -455,15 +666,30 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
         T cx[NP], cy[NP], cz[NP], vx[NP], vy[NP], vz[NP];
 #pragma unroll
         for (int u = 0; u < NP; ++u) { cx[u] = nx[u]; cy[u] = ny[u]; cz[u] = nz[u]; vx[u] = nvx[u]; vy[u] = nvy[u]; vz[u] = nvz[u]; }
-        if (i + 1 < P.N) {
-            load_packs<V>(nextp, nx); load_packs<V>(nextp + PK, ny); load_packs<V>(nextp + 2 * PK, nz);
-            load_packs<V>(nextp + 3 * PK, nvx); load_packs<V>(nextp + 4 * PK, nvy); load_packs<V>(nextp + 5 * PK, nvz);
+        SdfTile tile = { nullptr, 0, 0, 0 };
+        if constexpr (!TMA) {
+            if (i + 1 < P.N) {
+                load_packs<V>(nextp, nx); load_packs<V>(nextp + PK, ny); load_packs<V>(nextp + 2 * PK, nz);
+                load_packs<V>(nextp + 3 * PK, nvx); load_packs<V>(nextp + 4 * PK, nvy); load_packs<V>(nextp + 5 * PK, nvz);
+            }
+        } else {
+            if (i + 1 < P.N) {
+#pragma unroll
+                for (int u = 0; u < NP; ++u) { nx[u] = n2x[u]; ny[u] = n2y[u]; nz[u] = n2z[u]; }
+                load_packs<V>(nextp + 3 * PK, nvx); load_packs<V>(nextp + 4 * PK, nvy); load_packs<V>(nextp + 5 * PK, nvz);
+                if (i + 2 < P.N) { load_packs<V>(nextp + RS, n2x); load_packs<V>(nextp + RS + PK, n2y); load_packs<V>(nextp + RS + 2 * PK, n2z); }
+            }
+            const int b = i & 1;
+            tile.data = sm.tile[wid][b]; tile.ox = bx; tile.oy = by; tile.oz = bz;
+            if (i + 1 < P.N) sdf_stage_row<T, NP>(P, &sdf_map, sm, i + 1, nx, ny, nz, bx, by, bz);   // tile of row i+1 flies while row i is computed
+            mbar_wait(&sm.bar[wid][b], (phase >> b) & 1u);
+            phase ^= 1u << b;
         }
         T fvx[NP], fvy[NP], fvz[NP], odx[NP], ody[NP], odz[NP];
 #pragma unroll
         for (int u = 0; u < NP; ++u) {
-            if (GATHER) gather_pack<T>(P, fgrid, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u]);
-            const PointOut<T> o = point_update<T, WIND, NELL>(P, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
+            if (GATHER) gather_pack<T, GATHER == 2>(P, fgrid, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u]);
+            const PointOut<T> o = point_update<T, WIND, NELL>(P, tile, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
             parx[u] = o.px; pary[u] = o.py; parz[u] = o.pz;
             odx[u] = o.dx; ody[u] = o.dy; odz[u] = o.dz;
             // finalise point i-1: v_{i-1} -= d_i / dt   (compute.comp:213-215)
@@ -719,7 +945,7 @@ k_grid_finalize(const long long* __restrict__ grid, float4* __restrict__ fgrid, 
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (dens > 0) {
         const float rd = __frcp_rn(__ll2float_rn(dens));                 // 1.0 / float(density), compute.comp:283
-        o.x = __ll2float_rn(v0) * rd; o.y = __ll2float_rn(v1) * rd; o.z = __ll2float_rn(v2) * rd; o.w = rd;
+        o.x = __ll2float_rn(v0) * rd; o.y = __ll2float_rn(v1) * rd; o.z = __ll2float_rn(v2) * rd; o.w = __ll2float_rn(dens);
     }
     fgrid[k] = o;
 }
@@ -775,7 +1001,7 @@ k_grid_exchange(const ExchangePeers X, int rank, int nranks, int cells, int int3
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (dens > 0) {
             const float rd = __frcp_rn(__ll2float_rn(dens));
-            o.x = __ll2float_rn(v0) * rd; o.y = __ll2float_rn(v1) * rd; o.z = __ll2float_rn(v2) * rd; o.w = rd;
+            o.x = __ll2float_rn(v0) * rd; o.y = __ll2float_rn(v1) * rd; o.z = __ll2float_rn(v2) * rd; o.w = __ll2float_rn(dens);
         }
 #pragma unroll
         for (int r = 0; r < kMaxRanks; ++r) if (r < nranks) X.fgrid[r][k] = o;
@@ -802,6 +1028,7 @@ k_grid_exchange(const ExchangePeers X, int rank, int nranks, int cells, int int3
 // ---- K2: stand-alone grid gather + friction ------------------------------------------------------
 // Normally the gather of step k rides in k_ftl_step of step k+1; this kernel applies it when the state
 // is read back (download / interop pack) or a phase is requested explicitly.  One thread = one pack.
+template <bool REP>
 __global__ void __launch_bounds__(256)
 k_grid_gather(const __grid_constant__ StepParams P, float* __restrict__ planes, const float4* __restrict__ fgrid) {
     constexpr int plane = kTileStrands;
@@ -813,7 +1040,7 @@ k_grid_gather(const __grid_constant__ StepParams P, float* __restrict__ planes, 
         float* q = planes + tiled_index(6, P.S_pad, (int)row + 1, 0, (int)s0);   // skip the root row
         const float2 px = *reinterpret_cast<const float2*>(q), py = *reinterpret_cast<const float2*>(q + plane), pz = *reinterpret_cast<const float2*>(q + 2 * plane);
         float2 vx = *reinterpret_cast<const float2*>(q + 3 * plane), vy = *reinterpret_cast<const float2*>(q + 4 * plane), vz = *reinterpret_cast<const float2*>(q + 5 * plane);
-        gather_pack<float2>(P, fgrid, px, py, pz, vx, vy, vz);
+        gather_pack<float2, REP>(P, fgrid, px, py, pz, vx, vy, vz);
         *reinterpret_cast<float2*>(q + 3 * plane) = vx; *reinterpret_cast<float2*>(q + 4 * plane) = vy; *reinterpret_cast<float2*>(q + 5 * plane) = vz;
     }
 }
@@ -950,6 +1177,121 @@ __global__ void k_morton_keys(const float4* __restrict__ aos, int S, int N, floa
     const float fz = fminf(fmaxf((r.z - oz) * inv_extent, 0.f), 0.999999f) * 1024.f;
     keys[s] = part1by2((unsigned)fx) | (part1by2((unsigned)fy) << 1) | (part1by2((unsigned)fz) << 2);
     ids[s] = s;
+}
+
+
+// ---- head SDF bakes (extension; oracle twins: oracle.c orc_sdf_bake_colliders / orc_sdf_bake_mesh) ----------------
+// One thread per lattice node, node (i,j,k) at origin + cell*(i,j,k); padded columns i >= nx get a large positive value.
+constexpr float kSdfFar = 1.0e9f;
+
+// Signed radial distance to the union of the ellipsoid colliders: for ellipsoid E, q = inv*(p,1), on = T*(q/|q|, 1),
+// |on - p| is the penetration depth the shader uses (compute.comp:171-172); negative where |q| <= 1.
+__global__ void __launch_bounds__(256)
+k_sdf_bake_colliders(const __grid_constant__ StepParams P, float* __restrict__ out, int nx, int ny, int nz, int nxp,
+                     float ox, float oy, float oz, float cell) {
+    const size_t total = (size_t)nxp * ny * nz;
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const int i = (int)(k % nxp), j = (int)((k / nxp) % ny), kk = (int)(k / ((size_t)nxp * ny));
+    if (i >= nx) { out[k] = kSdfFar; return; }
+    const float px = ox + cell * (float)i, py = oy + cell * (float)j, pz = oz + cell * (float)kk;
+    float best = kSdfFar;
+    for (int e = 0; e < P.n_ell; ++e) {
+        const Ellipsoid& E = P.ell[e];
+        float qx, qy, qz;
+        const float q2 = ellipsoid_q<float>(E, px, py, pz, qx, qy, qz);
+        float ux = 1.f, uy = 0.f, uz = 0.f;
+        if (q2 > 0.f) { const float r = 1.0f / sqrtf(q2); ux = qx * r; uy = qy * r; uz = qz * r; }
+        const float sx = fmaf(E.xf[0], ux, fmaf(E.xf[1], uy, fmaf(E.xf[2], uz, E.xf[3])));
+        const float sy = fmaf(E.xf[4], ux, fmaf(E.xf[5], uy, fmaf(E.xf[6], uz, E.xf[7])));
+        const float sz = fmaf(E.xf[8], ux, fmaf(E.xf[9], uy, fmaf(E.xf[10], uz, E.xf[11])));
+        const float ex = px - sx, ey = py - sy, ez = pz - sz;
+        const float dist = sqrtf(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
+        best = fminf(best, q2 <= 1.0f ? -dist : dist);
+    }
+    out[k] = best;
+}
+
+// Squared distance from p to triangle (a, b, c): closest-point regions of Ericson, Real-Time Collision Detection 5.1.5.
+__device__ __forceinline__ float tri_dist2(float px, float py, float pz, const float* t) {
+    const float ax = t[0], ay = t[1], az = t[2];
+    const float abx = t[3] - ax, aby = t[4] - ay, abz = t[5] - az;
+    const float acx = t[6] - ax, acy = t[7] - ay, acz = t[8] - az;
+    const float apx = px - ax, apy = py - ay, apz = pz - az;
+    const float d1 = abx * apx + aby * apy + abz * apz, d2 = acx * apx + acy * apy + acz * apz;
+    float cx, cy, cz;                                    // closest point - a
+    if (d1 <= 0.f && d2 <= 0.f) { cx = 0.f; cy = 0.f; cz = 0.f; }
+    else {
+        const float bpx = apx - abx, bpy = apy - aby, bpz = apz - abz;
+        const float d3 = abx * bpx + aby * bpy + abz * bpz, d4 = acx * bpx + acy * bpy + acz * bpz;
+        if (d3 >= 0.f && d4 <= d3) { cx = abx; cy = aby; cz = abz; }
+        else {
+            const float vc = d1 * d4 - d3 * d2;
+            if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { const float v = d1 / (d1 - d3); cx = v * abx; cy = v * aby; cz = v * abz; }
+            else {
+                const float cpx = apx - acx, cpy = apy - acy, cpz = apz - acz;
+                const float d5 = abx * cpx + aby * cpy + abz * cpz, d6 = acx * cpx + acy * cpy + acz * cpz;
+                if (d6 >= 0.f && d5 <= d6) { cx = acx; cy = acy; cz = acz; }
+                else {
+                    const float vb = d5 * d2 - d1 * d6;
+                    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { const float w = d2 / (d2 - d6); cx = w * acx; cy = w * acy; cz = w * acz; }
+                    else {
+                        const float va = d3 * d6 - d5 * d4;
+                        if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+                            const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+                            cx = abx + w * (acx - abx); cy = aby + w * (acy - aby); cz = abz + w * (acz - abz);
+                        } else {
+                            const float den = 1.0f / (va + vb + vc);
+                            const float v = vb * den, w = vc * den;
+                            cx = abx * v + acx * w; cy = aby * v + acy * w; cz = abz * v + acz * w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const float ex = apx - cx, ey = apy - cy, ez = apz - cz;
+    return ex * ex + ey * ey + ez * ez;
+}
+
+// Solid angle of the triangle seen from p (Van Oosterom & Strackee 1983): 2*atan2(a.(b x c), |a||b||c| + (a.b)|c| + (b.c)|a| + (c.a)|b|).
+__device__ __forceinline__ float tri_solid_angle(float px, float py, float pz, const float* t) {
+    const float ax = t[0] - px, ay = t[1] - py, az = t[2] - pz;
+    const float bx = t[3] - px, by = t[4] - py, bz = t[5] - pz;
+    const float cx = t[6] - px, cy = t[7] - py, cz = t[8] - pz;
+    const float la = sqrtf(ax * ax + ay * ay + az * az), lb = sqrtf(bx * bx + by * by + bz * bz), lc = sqrtf(cx * cx + cy * cy + cz * cz);
+    const float num = ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
+    const float den = la * lb * lc + (ax * bx + ay * by + az * bz) * lc + (bx * cx + by * cy + bz * cz) * la + (cx * ax + cy * ay + cz * az) * lb;
+    return 2.0f * atan2f(num, den);
+}
+
+// Brute force over all triangles (staged through shared memory 128 at a time): the mannequin has a few thousand
+// triangles and the lattice ~1M nodes, i.e. a few G point-triangle tests, tens of milliseconds on a B200, once.
+// Sign: |generalized winding number| > 1/2 (Jacobson et al. 2013) -- well defined for the open-necked mesh.
+constexpr int kBakeTris = 128;
+__global__ void __launch_bounds__(256)
+k_sdf_bake_mesh(float* __restrict__ out, int nx, int ny, int nz, int nxp, float ox, float oy, float oz, float cell,
+                const float* __restrict__ tri9, int ntris) {
+    __shared__ float st[kBakeTris * 9];
+    const size_t total = (size_t)nxp * ny * nz;
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = k < total;
+    const int i = live ? (int)(k % nxp) : 0, j = live ? (int)((k / nxp) % ny) : 0, kk = live ? (int)(k / ((size_t)nxp * ny)) : 0;
+    const float px = ox + cell * (float)i, py = oy + cell * (float)j, pz = oz + cell * (float)kk;
+    float best2 = 3.0e38f, omega = 0.f;
+    for (int t0 = 0; t0 < ntris; t0 += kBakeTris) {
+        const int cnt = min(kBakeTris, ntris - t0);
+        __syncthreads();
+        for (int q = threadIdx.x; q < cnt * 9; q += blockDim.x) st[q] = tri9[(size_t)t0 * 9 + q];
+        __syncthreads();
+        for (int t = 0; t < cnt; ++t) {
+            best2 = fminf(best2, tri_dist2(px, py, pz, st + 9 * t));
+            omega += tri_solid_angle(px, py, pz, st + 9 * t);
+        }
+    }
+    if (!live) return;
+    const float d = sqrtf(best2);
+    out[k] = i >= nx ? kSdfFar : (fabsf(omega) > 6.2831855f ? -d : d);     // |omega / 4pi| > 1/2
 }
 
 }  // namespace rvh

@@ -11,6 +11,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 
 GRID_ON, WIND_A, WIND_B, GRID_INT32_WRAP = 1, 2, 4, 8
+SDF_ON, REPULSION_ON = 64, 128          # extensions (not in the reference), see oracle.h
 
 
 class OrcParams(C.Structure):
@@ -19,7 +20,7 @@ class OrcParams(C.Structure):
         ("gravity_y", C.c_float), ("damping", C.c_float), ("vmax", C.c_float),
         ("penalty_k", C.c_float), ("sphere_radius", C.c_float), ("grid_dim", C.c_int),
         ("grid_extent", C.c_float), ("grid_origin", C.c_float * 3), ("grid_scale", C.c_float),
-        ("friction", C.c_float), ("flags", C.c_int), ("num_colliders", C.c_int),
+        ("friction", C.c_float), ("flags", C.c_int), ("num_colliders", C.c_int), ("repulsion", C.c_float),
     ]
 
 
@@ -60,6 +61,12 @@ def lib():
         L.orc_step_parallel.argtypes = [C.POINTER(OrcParams), _fp, C.c_float, C.c_float, _fp, _i64p, C.c_int]
         L.orc_max_threads.restype = C.c_int
         L.orc_init_strands_reference.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp]
+        _ip = C.POINTER(C.c_int)
+        L.orc_set_head_sdf.argtypes = [_fp, _ip, _fp, C.c_float]
+        L.orc_sdf_sample.argtypes = [_fp, _fp, _fp]
+        L.orc_sdf_sample.restype = C.c_int
+        L.orc_sdf_bake_colliders.argtypes = [_fp, C.c_int, _ip, _fp, C.c_float, _fp]
+        L.orc_sdf_bake_mesh.argtypes = [_fp, _ip, C.c_int, _ip, _fp, C.c_float, _fp]
         _lib = L
     return _lib
 
@@ -141,6 +148,52 @@ def init_strands_reference(roots, normals, N):
     n = np.ascontiguousarray(normals, np.float32)
     lib().orc_init_strands_reference(S, N, _f(r), _f(n), _f(st))
     return st
+
+
+# ---- extensions: head SDF ----------------------------------------------------------------
+
+_sdf_keep = None
+
+
+def set_head_sdf(vol, origin, cell):
+    """vol: float32 [nz][ny][nx] (None clears).  The oracle keeps a pointer, so the array is pinned here."""
+    global _sdf_keep
+    if vol is None:
+        lib().orc_set_head_sdf(None, None, None, 0.0)
+        _sdf_keep = None
+        return
+    v = np.ascontiguousarray(vol, np.float32)
+    dim = np.array([v.shape[2], v.shape[1], v.shape[0]], np.int32)
+    o = np.asarray(origin, np.float32).copy()
+    _sdf_keep = (v, dim, o)
+    lib().orc_set_head_sdf(_f(v), dim.ctypes.data_as(C.POINTER(C.c_int)), _f(o), C.c_float(cell))
+
+
+def sdf_sample(p):
+    pp = np.asarray(p, np.float32).copy()
+    d = np.zeros(1, np.float32)
+    g = np.zeros(3, np.float32)
+    ok = lib().orc_sdf_sample(_f(pp), _f(d), _f(g))
+    return bool(ok), float(d[0]), g
+
+
+def sdf_bake_colliders(colliders, dim, origin, cell):
+    col = np.ascontiguousarray(colliders, np.float32).reshape(-1, 48)
+    d = np.asarray(dim, np.int32).copy()
+    o = np.asarray(origin, np.float32).copy()
+    out = np.zeros((d[2], d[1], d[0]), np.float32)
+    lib().orc_sdf_bake_colliders(_f(col), col.shape[0], d.ctypes.data_as(C.POINTER(C.c_int)), _f(o), C.c_float(cell), _f(out))
+    return out
+
+
+def sdf_bake_mesh(verts, tris, dim, origin, cell):
+    v = np.ascontiguousarray(verts, np.float32)
+    t = np.ascontiguousarray(tris, np.int32)
+    d = np.asarray(dim, np.int32).copy()
+    o = np.asarray(origin, np.float32).copy()
+    out = np.zeros((d[2], d[1], d[0]), np.float32)
+    lib().orc_sdf_bake_mesh(_f(v), t.ctypes.data_as(C.POINTER(C.c_int)), t.shape[0], d.ctypes.data_as(C.POINTER(C.c_int)), _f(o), C.c_float(cell), _f(out))
+    return out
 
 
 # ---- oracle/_ref: the reference's own sources compiled here ---------------------------

@@ -29,12 +29,12 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(rvh.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.rvh_abi_version() == 1
+    assert L.rvh_abi_version() == 2
 
 
 def test_struct_sizes_match_reference_layouts():
     # Strand = 48*N bytes, Collider = 192, GridCell = 16, StrandDrawIndirect = 16 (Strand.h, Scene.h)
-    assert C.sizeof(rvh.RvhConfig) == 4 * 18
+    assert C.sizeof(rvh.RvhConfig) == 4 * 19
     cfg = rvh.default_config(900, 10)
     assert cfg.num_strands * 48 * cfg.num_points == 432000          # Renderer.cpp:967 descriptor range
     assert abs(cfg.rest_length - np.float32(2.5) / np.float32(9.0)) == 0
