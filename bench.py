@@ -248,6 +248,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: every rank owns the workload's strand count; strong: the count is split over the ranks")
+    ap.add_argument("--expand", action="store_true", help="also time the guide -> render strand expansion (hair.tesc/hair.tese, 12 isolines x 42 divisions) of the final state")
     ap.add_argument("--device-init", action="store_true", help="generate the synthetic head on the GPU (rvh_init_synthetic_head) instead of uploading it")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -396,6 +397,14 @@ def main():
         e2e_resident = {"value": S_total * N * n_res / el, "unit": UNIT,
                         "h2d_bytes_per_step": cols.nbytes + 8, "d2h_bytes_per_step": 16, "steps": n_res,
                         "what": "per-frame API as the reference drives it: rvh_set_colliders (UBO) + rvh_step + rvh_draw_indirect read-back; strand state resident"}
+    expand = None
+    if args.expand:
+        sim.expand(12, 42, download=False)                                   # allocation + tables
+        times = [sim.expand(12, 42, download=False)[2] for _ in range(5)]
+        verts = S * 12 * 43
+        ems = statistics.median(times)
+        expand = {"isolines": 12, "divisions": 42, "vertices": verts, "ms": ems, "vertices_per_s": verts / (ems * 1e-3),
+                  "write_GBps": verts * 32 / (ems * 1e-3) / 1e9, "what": "k_expand_strands: 2 x float4 per vertex written, guide positions read once (per GPU)"}
     sim.close()
 
     cpu = None
@@ -421,6 +430,8 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_resident,
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if expand is not None:
+        out["expand"] = expand
     print(json.dumps(out), flush=True)
     return 0
 

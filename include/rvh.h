@@ -141,6 +141,20 @@ int rvh_bake_head_sdf_from_mesh(rvh_ctx* ctx, const float* verts, int nverts, co
 int rvh_download_head_sdf(rvh_ctx* ctx, float* sdf, size_t bytes);     /* nx*ny*nz floats */
 int rvh_sdf_mode(rvh_ctx* ctx);   /* 0 = no volume, 1 = plain loads (default), 2 = TMA-staged tiles (RVH_SDF_TMA) */
 
+/* ---- guide strands -> render strands -------------------------------------------------
+ * What the reference's tessellator does with the simulated buffer: every guide strand is one patch, expanded into
+ * `isolines` x `divisions` line segments (12 x 42, hair.tesc:19-20) whose vertices hair.tese places by Bezier
+ * interpolation along the guide plus a sideways deviation (hair.tese:34-80, 226-304).  This produces the same
+ * vertices headless, as line strips: two float4 per vertex, arrays [S][isolines][divisions+1] in the caller's strand
+ * order -- pos_width = (position, strand width hair.tese:313-315), tangent_u = (unit tangent of the guide segment
+ * hair.tese:267, isoline coordinate u).  Host pointers may be NULL (results stay on the device,
+ * rvh_expand_device_buffers); ms_out, if given, receives the kernel time (CUDA events).  Deviations: the fract(sin)
+ * hashes take the sine in double precision so that CPU and GPU agree; at v = 1 the shader reads one curve point past
+ * the end (hair.tese:165-166), here the last vertex is the guide's last point; model matrix = identity as Hair::Hair
+ * sets it (Strand.cpp:183-185). */
+int rvh_expand_strands(rvh_ctx* ctx, int isolines, int divisions, float* pos_width, float* tangent_u, size_t bytes_each, float* ms_out);
+int rvh_expand_device_buffers(rvh_ctx* ctx, void** pos_width, void** tangent_u, size_t* vertices);
+
 /* Vulkan interop: map the exported strands VkBuffer (VK_KHR_external_memory_fd) and
  * keep it updated after every step in the reference's AoS vertex-buffer layout
  * (Renderer.cpp:2153-2161 binds it).  Needs a Vulkan device on the caller's side. */

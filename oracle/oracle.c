@@ -684,3 +684,69 @@ void orc_sdf_bake_mesh(const float* verts, const int* tris, int ntris, const int
                 out[i + (size_t)dim[0] * (j + (size_t)dim[1] * k)] = fabsf(omega) > 6.2831855f ? -d : d;   /* |winding| > 1/2 */
             }
 }
+
+/* ---- hair.tese restated (vertex placement only; shading outputs depend on the cameras) ------ */
+
+static float tese_random(float x, float y) {                /* hair.tese:30-32, sine in double */
+    const float a = x * 12.9898f, b = y * 78.233f;
+    const float d = a + b;
+    const float h = (float)sin((double)d) * 43758.5453123f;
+    return h - floorf(h);
+}
+static float tese_mix(float a, float b, float t) { return a + t * (b - a); }
+
+void orc_expand_strands(const float* strands, int S, int N, int isolines, int divisions,
+                        float* pos_width, float* tangent_u) {
+    const float PI = 3.141592653f;                          /* hair.tese:3 */
+    #pragma omp parallel for schedule(static)
+    for (int s = 0; s < S; ++s) {
+        const float* P = strands + (size_t)s * 12 * N;      /* curvePoints[N] as vec4 */
+        for (int k = 0; k < isolines; ++k) {
+            const float u = (float)k / (float)isolines;     /* gl_TessCoord.y */
+            const float rand2 = fabsf(tese_random(u, u * u));                   /* :226 */
+            const float uRad = 2.0f * PI * u;                                   /* :235 */
+            const float cx = cosf(uRad), sz = sinf(uRad);
+            const float len = sqrtf(cx * cx + sz * sz);
+            const float dirx = cx / len, dirz = sz / len;                       /* :236 */
+            const float choice = tese_random(u, P[0]) * tese_random(P[1], P[2]); /* :245 */
+            for (int j = 0; j <= divisions; ++j) {
+                const float v = (float)j / (float)divisions; /* gl_TessCoord.x */
+                const float vs = v * (float)(N - 1);
+                int seg = (int)floorf(vs);                                       /* :40, :165 */
+                if (seg > N - 2) seg = N - 2;               /* v = 1: the shader reads point N */
+                const float t = vs - (float)seg;                                /* :65 */
+                float c[3], tg[3];
+                for (int a = 0; a < 3; ++a) {               /* func(), :34-80 */
+                    const float v1 = P[4 * seg + a], v2 = P[4 * (seg + 1) + a];
+                    const float v0 = seg == 0 ? v1 + (v1 - v2) : P[4 * (seg - 1) + a];
+                    const float v3 = seg + 1 == N - 1 ? v2 + (v2 - v1) : P[4 * (seg + 2) + a];
+                    const float b1 = v1 + (1.0f / 3.0f) * ((v2 - v0) / 2.0f);
+                    const float b2 = v2 - (1.0f / 3.0f) * ((v3 - v1) / 2.0f);
+                    const float b01 = tese_mix(v1, b1, t), b11 = tese_mix(b1, b2, t), b21 = tese_mix(b2, v2, t);
+                    const float b02 = tese_mix(b01, b11, t), b12 = tese_mix(b11, b21, t);
+                    c[a] = tese_mix(b02, b12, t);
+                    tg[a] = v2 - v1;                                            /* :267 */
+                }
+                float width = 0.5f * tese_mix(tese_mix(0.05f, 0.3f, v), tese_mix(0.3f, 0.1f, v), v) * (rand2 + 0.5f);   /* :228-229 */
+                float sd = 1.0f;                                                /* :239-269 */
+                const float two_s2 = 2.0f * powf(0.2f, 2.0f);
+                if (choice > 0.5f) {
+                    if (choice > 0.9f) sd = 1.8f * expf(-powf(v - 0.25f, 2.0f) / two_s2);
+                    else if (choice > 0.8f) sd = 4.5f * powf(v, 10.0f);
+                    else if (choice > 0.7f) sd = 2.5f * expf(-powf(v - 0.7f, 2.0f) / two_s2);
+                    else if (choice > 0.6f) sd = 4.0f * powf(v, 1.3f);
+                    else sd = 1.8f * expf(-powf(v - 0.8f, 2.0f) / two_s2);
+                }
+                if (v == 0.0f) sd = 1.0f;
+                const size_t o = (((size_t)s * isolines + k) * (size_t)(divisions + 1) + j) * 4;
+                pos_width[o]     = c[0] + width * (dirx * sd);                  /* :278, :304 */
+                pos_width[o + 1] = c[1] + width * (0.0f * sd);
+                pos_width[o + 2] = c[2] + width * (dirz * sd);
+                pos_width[o + 3] = tese_mix(0.02f, 0.01f, v);                   /* :313-315 */
+                const float tl = sqrtf(tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2]);
+                tangent_u[o] = tg[0] / tl; tangent_u[o + 1] = tg[1] / tl; tangent_u[o + 2] = tg[2] / tl;
+                tangent_u[o + 3] = u;
+            }
+        }
+    }
+}

@@ -114,6 +114,14 @@ void orc_sdf_bake_colliders(const float* colliders48, int num_colliders, const i
 void orc_sdf_bake_mesh(const float* verts, const int* tris, int ntris, const int dim[3],
                        const float origin[3], float cell, float* out);
 
+/* ---- guide strand -> render strands: hair.tesc:19-20 + hair.tese -------
+ * CPU restatement of what the tessellator + hair.tese emit for every guide strand: `isolines`
+ * line strips of divisions+1 vertices.  pos_width / tangent_u are float [S][isolines][divisions+1][4].
+ * Stated choices (the product makes the same ones, include/rvh.h): sine of the fract(sin) hash in
+ * double precision; last vertex (v = 1) = last curve point; model matrix = identity. */
+void orc_expand_strands(const float* strands, int S, int N, int isolines, int divisions,
+                        float* pos_width, float* tangent_u);
+
 /* Hair::Hair initial state (Strand.cpp:157-175) from follicle roots + normals. */
 void orc_init_strands_reference(int S, int N, const float* roots3, const float* normals3,
                                 float* strands);

@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "rvh_profile_enable", "rvh_profile_read", "rvh_sync", "rvh_last_step_ms", "rvh_kernel_launches",
     "rvh_last_error", "rvh_destroy", "rvh_collider_build", "rvh_collider_translate", "rvh_wind_fbm",
     "rvh_abi_version", "rvh_set_head_sdf", "rvh_bake_head_sdf_from_colliders", "rvh_bake_head_sdf_from_mesh",
-    "rvh_download_head_sdf", "rvh_sdf_mode",
+    "rvh_download_head_sdf", "rvh_sdf_mode", "rvh_expand_strands", "rvh_expand_device_buffers",
 ]
 
 
@@ -91,6 +91,8 @@ def load_library():
     L.rvh_bake_head_sdf_from_mesh.argtypes = [vp, fp, C.c_int, ip, C.c_int, ip, fp, C.c_float]
     L.rvh_download_head_sdf.argtypes = [vp, fp, C.c_size_t]
     L.rvh_sdf_mode.argtypes = [vp]
+    L.rvh_expand_strands.argtypes = [vp, C.c_int, C.c_int, fp, fp, C.c_size_t, fp]
+    L.rvh_expand_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     _lib = L
     return L
 
@@ -272,6 +274,17 @@ class HairSim:
 
     def sdf_mode(self):
         return {0: "off", 1: "ldg", 2: "tma"}[int(self.L.rvh_sdf_mode(self.ctx))]
+
+    def expand(self, isolines=12, divisions=42, download=True):
+        """Guide -> render strands (hair.tesc/hair.tese).  Returns (pos_width, tangent_u, ms); arrays [S, isolines, divisions+1, 4]."""
+        ms = C.c_float(0.0)
+        if not download:
+            self._check(self.L.rvh_expand_strands(self.ctx, isolines, divisions, None, None, 0, C.byref(ms)), "rvh_expand_strands")
+            return None, None, float(ms.value)
+        pw = np.empty((self.S, isolines, divisions + 1, 4), np.float32)
+        tu = np.empty_like(pw)
+        self._check(self.L.rvh_expand_strands(self.ctx, isolines, divisions, _fptr(pw), _fptr(tu), pw.nbytes, C.byref(ms)), "rvh_expand_strands")
+        return pw, tu, float(ms.value)
 
     def exchange_mode(self):
         return {0: "single", 1: "nccl-allreduce", 2: "peer-memory-fused"}[int(self.L.rvh_exchange_mode(self.ctx))]

@@ -81,6 +81,9 @@ struct rvh_ctx {
     int sdf_mode = 0;                     // 0 = no volume, 1 = plain loads, 2 = TMA-staged tiles
     CUtensorMap sdf_map;                  // 3-D tiled map of the volume, box 8x4x4 nodes (zeroed when unused)
     float* bake_tris = nullptr;
+    // guide -> render strand expansion (k_expand_strands)
+    ExpandTables* exp_tab = nullptr; int exp_I = 0, exp_D = 0;
+    float4* exp_pw = nullptr; float4* exp_tu = nullptr; size_t exp_cap = 0;   // vertices allocated
     float sdf_cell = 0.f;
     // multi-GPU
     int rank = 0, nranks = 1;
@@ -637,6 +640,91 @@ int rvh_download_head_sdf(rvh_ctx* ctx, float* sdf, size_t bytes) {
 int rvh_sdf_mode(rvh_ctx* ctx) { return ctx ? ctx->sdf_mode : 0; }
 
 
+// ---- guide strand -> render strands (hair.tesc / hair.tese) -------------------------------------------------
+static float mixh(float a, float b, float t) { return a + t * (b - a); }
+
+// Everything of hair.tese that depends on the isoline (u) or the division (v) alone; see ExpandTables.
+static void build_expand_tables(int N, int I, int D, ExpandTables& T) {
+    std::memset(&T, 0, sizeof T);
+    for (int j = 0; j <= D; ++j) {
+        const float v = (float)j / (float)D;                                   // gl_TessCoord.x of an isoline with D segments
+        const float vs = v * (float)(N - 1);                                   // hair.tese:165
+        int seg = (int)std::floor(vs);
+        if (seg > N - 2) seg = N - 2;                                          // v = 1: the shader would index point N
+        T.seg[j] = seg;
+        T.t[j] = vs - (float)seg;                                              // :216
+        T.width[j] = 0.5f * mixh(mixh(0.05f, 0.3f, v), mixh(0.3f, 0.1f, v), v);   // :228-229 (clumpRadius = 0.5)
+        T.strand_width[j] = mixh(0.02f, 0.01f, v);                             // :313-315
+        const float two_s2 = 2.0f * std::pow(0.2f, 2.0f);
+        T.sd[0][j] = 1.0f;
+        T.sd[1][j] = 1.8f * std::exp(-std::pow(v - 0.25f, 2.0f) / two_s2);     // :248
+        T.sd[2][j] = 4.5f * std::pow(v, 10.0f);                                // :250
+        T.sd[3][j] = 2.5f * std::exp(-std::pow(v - 0.7f, 2.0f) / two_s2);      // :252
+        T.sd[4][j] = 4.0f * std::pow(v, 1.3f);                                 // :254
+        T.sd[5][j] = 1.8f * std::exp(-std::pow(v - 0.8f, 2.0f) / two_s2);      // :256
+        if (v == 0.0f) for (int f = 0; f < 6; ++f) T.sd[f][j] = 1.0f;          // :267-269
+    }
+    for (int k = 0; k < I; ++k) {
+        const float u = (float)k / (float)I;                                   // gl_TessCoord.y: isoline k of I
+        T.u[k] = u;
+        const float uRad = 2.0f * 3.141592653f * u;                            // :235
+        const float c = std::cos(uRad), sn = std::sin(uRad);
+        const float len = std::sqrt(c * c + sn * sn);
+        T.dirx[k] = c / len; T.dirz[k] = sn / len;                             // :236
+        T.wr[k] = std::fabs(expand_hash(u, u * u)) + 0.5f;                     // rand2 + 0.5, :226,229
+    }
+}
+
+int rvh_expand_strands(rvh_ctx* ctx, int isolines, int divisions, float* pos_width, float* tangent_u, size_t bytes_each, float* ms_out) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!ctx->uploaded) return fail(ctx, RVH_ERR_STATE, "rvh_expand_strands before any strands were uploaded");
+    if (isolines < 1 || isolines > kMaxIsolines || divisions < 1 || divisions > kMaxDivisions) return fail(ctx, RVH_ERR_INVALID, "1 <= isolines <= 64, 1 <= divisions <= 256");
+    const size_t verts = (size_t)ctx->S * isolines * (divisions + 1);
+    if ((pos_width || tangent_u) && bytes_each != verts * 16) return fail(ctx, RVH_ERR_INVALID, "each output must be S*isolines*(divisions+1)*16 bytes");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->exp_tab || ctx->exp_I != isolines || ctx->exp_D != divisions) {
+        ExpandTables T;
+        build_expand_tables(ctx->N, isolines, divisions, T);
+        if (!ctx->exp_tab) CU(cudaMalloc(&ctx->exp_tab, sizeof(ExpandTables)));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(ctx->exp_tab, &T, sizeof T, cudaMemcpyHostToDevice));
+        ctx->exp_I = isolines; ctx->exp_D = divisions;
+    }
+    if (ctx->exp_cap < verts) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->exp_pw); cudaFree(ctx->exp_tu); ctx->exp_pw = ctx->exp_tu = nullptr; ctx->exp_cap = 0;
+        CU(cudaMalloc(&ctx->exp_pw, verts * sizeof(float4)));
+        CU(cudaMalloc(&ctx->exp_tu, verts * sizeof(float4)));
+        ctx->exp_cap = verts;
+    }
+    const size_t sm = (size_t)3 * ctx->N * (kExpandTile + 1) * sizeof(float) + (size_t)kExpandTile * isolines;
+    CU(cudaFuncSetAttribute(k_expand_strands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const bool reorder = ctx->perm != nullptr && !(ctx->cfg.flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
+    if (ms_out) CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+    k_expand_strands<<<(ctx->S + kExpandTile - 1) / kExpandTile, 256, sm, ctx->stream>>>(ctx->planes, reorder ? ctx->perm : nullptr, ctx->exp_tab, ctx->exp_pw, ctx->exp_tu,
+                                                                                          ctx->S, ctx->S_pad, ctx->N, isolines, divisions);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    if (ms_out) {
+        CU(cudaEventRecord(ctx->ev_b, ctx->stream));
+        CU(cudaEventSynchronize(ctx->ev_b));
+        CU(cudaEventElapsedTime(ms_out, ctx->ev_a, ctx->ev_b));
+    }
+    if (pos_width) CU(cudaMemcpyAsync(pos_width, ctx->exp_pw, verts * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tangent_u) CU(cudaMemcpyAsync(tangent_u, ctx->exp_tu, verts * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pos_width || tangent_u) CU(cudaStreamSynchronize(ctx->stream));
+    return RVH_OK;
+}
+
+int rvh_expand_device_buffers(rvh_ctx* ctx, void** pos_width, void** tangent_u, size_t* vertices) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!ctx->exp_pw) return fail(ctx, RVH_ERR_STATE, "rvh_expand_strands has not run");
+    if (pos_width) *pos_width = ctx->exp_pw;
+    if (tangent_u) *tangent_u = ctx->exp_tu;
+    if (vertices) *vertices = (size_t)ctx->S * ctx->exp_I * (ctx->exp_D + 1);
+    return RVH_OK;
+}
+
 int rvh_import_strands_fd(rvh_ctx* ctx, int fd, size_t bytes) {
     if (!ctx) return RVH_ERR_INVALID;
     if (bytes < ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "imported buffer smaller than Strand[S]");
@@ -768,7 +856,7 @@ void rvh_destroy(rvh_ctx* c) {
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->interop_aos) cudaFree(c->interop_aos);
     if (c->interop_mem) cudaDestroyExternalMemory(c->interop_mem);
-    cudaFree(c->sdf_dev); cudaFree(c->bake_tris);
+    cudaFree(c->sdf_dev); cudaFree(c->bake_tris); cudaFree(c->exp_tab); cudaFree(c->exp_pw); cudaFree(c->exp_tu);
     cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->fgrid); cudaFree(c->perm); cudaFree(c->aos_dev);
     cudaFree(c->sort_tmp); cudaFree(c->sort_keys); cudaFree(c->sort_keys_out); cudaFree(c->sort_ids);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);

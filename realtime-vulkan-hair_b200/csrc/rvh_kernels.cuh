@@ -1294,4 +1294,91 @@ k_sdf_bake_mesh(float* __restrict__ out, int nx, int ny, int nz, int nxp, float 
     out[k] = i >= nx ? kSdfFar : (fabsf(omega) > 6.2831855f ? -d : d);     // |omega / 4pi| > 1/2
 }
 
+// ---- guide strand -> render strands: hair.tesc + hair.tese on the tessellator ---------------
+// The reference draws every guide strand as ONE patch that the fixed-function tessellator expands into 12 isolines x 42
+// segments (hair.tesc:19-20); hair.tese places each generated vertex: Bezier interpolation along the guide (func(),
+// hair.tese:34-80) displaced sideways by width * dir (the multi-strand weights computed at :173-214 are dead:
+// `pos = singleStrandPos`, :304).  This kernel produces the same vertices as a line-strip buffer, headless:
+//     pos_width[e][k][j] = (func(u_k, v_j) + width_j * wr_k * sd_form(e,k)[j] * dir_k,  mix(0.02, 0.01, v_j))     :226-304, 313-315
+//     tangent_u[e][k][j] = (normalize(P[seg+1] - P[seg]), u_k)                                                    :267, 275
+// e = external strand index, u_k = k / isolines, v_j = j / divisions.  Everything that depends on (k) or (j) alone --
+// the fract(sin()) hashes of u, the Gaussian / power profiles of v, segment index and Bezier parameter -- is tabulated
+// on the host (ExpandTables); the only per-strand transcendental is the `randomChoice` hash of the root (:245), evaluated
+// as float(sin(double)) so that CPU oracle and GPU pick the same deviation profile.  Deviation from the shader: at v = 1
+// the shader indexes curve point N (out of bounds, :165-166); here the last vertex is the guide's last point.
+constexpr int kMaxIsolines = 64, kMaxDivisions = 256, kExpandTile = 32;
+struct ExpandTables {
+    int seg[kMaxDivisions + 1];            // floor(v * (N-1)) clamped to N-2
+    float t[kMaxDivisions + 1];            // Bezier parameter inside the segment
+    float width[kMaxDivisions + 1];        // clumpRadius * mix(mix(.05,.3,v), mix(.3,.1,v), v)          :229
+    float strand_width[kMaxDivisions + 1]; // mix(rootWidth, tipWidth, v)                                 :313-315
+    float sd[6][kMaxDivisions + 1];        // deviation profiles: 0 none, 1..5 the branches of :247-259
+    float u[kMaxIsolines], dirx[kMaxIsolines], dirz[kMaxIsolines], wr[kMaxIsolines];   // u_k, normalize(cos, 0, sin)(2 pi u), rand2 + 0.5
+};
+
+// random() of hair.tese:30-32 with the sine taken in double precision (see above)
+__host__ __device__ inline float expand_hash(float x, float y) {
+#ifdef __CUDA_ARCH__
+    const float d = __fadd_rn(__fmul_rn(x, 12.9898f), __fmul_rn(y, 78.233f));
+    const float h = __fmul_rn((float)sin((double)d), 43758.5453123f);
+#else
+    const float a = x * 12.9898f, b = y * 78.233f;
+    const float d = a + b;
+    const float h = (float)sin((double)d) * 43758.5453123f;
+#endif
+    return h - floorf(h);
+}
+__host__ __device__ inline int expand_form(float u, float rx, float ry, float rz) {     // hair.tese:245-259
+    const float choice = expand_hash(u, rx) * expand_hash(ry, rz);
+    return choice > 0.9f ? 1 : choice > 0.8f ? 2 : choice > 0.7f ? 3 : choice > 0.6f ? 4 : choice > 0.5f ? 5 : 0;
+}
+
+__device__ __forceinline__ float mixf(float a, float b, float t) { return fmaf(t, b - a, a); }
+
+__global__ void __launch_bounds__(256)
+k_expand_strands(const float* __restrict__ planes, const int* __restrict__ perm, const ExpandTables* __restrict__ tab,
+                 float4* __restrict__ pos_width, float4* __restrict__ tangent_u, int S, int S_pad, int N, int I, int D) {
+    extern __shared__ float esm[];
+    float* pos = esm;                                        // [3][N][kExpandTile + 1]
+    unsigned char* form = reinterpret_cast<unsigned char*>(pos + 3 * N * (kExpandTile + 1));   // [kExpandTile][I]
+    const int s0 = blockIdx.x * kExpandTile;
+    for (int q = threadIdx.x; q < 3 * N * kExpandTile; q += blockDim.x) {
+        const int sl = q % kExpandTile, r = q / kExpandTile;      // r = k*N + row
+        const int k = r / N, row = r % N;
+        pos[r * (kExpandTile + 1) + sl] = (s0 + sl < S_pad) ? planes[tiled_index(6, S_pad, row, k, s0 + sl)] : 0.f;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < kExpandTile * I; q += blockDim.x) {
+        const int sl = q / I, k = q % I;
+        form[q] = (unsigned char)expand_form(tab->u[k], pos[(0 * N) * (kExpandTile + 1) + sl], pos[(1 * N) * (kExpandTile + 1) + sl], pos[(2 * N) * (kExpandTile + 1) + sl]);
+    }
+    __syncthreads();
+    const int per = I * (D + 1);
+    for (int q = threadIdx.x; q < kExpandTile * per; q += blockDim.x) {
+        const int sl = q / per, rem = q - sl * per, k = rem / (D + 1), j = rem - k * (D + 1);
+        const int s = s0 + sl;
+        if (s >= S) continue;
+        const int seg = tab->seg[j];
+        const float t = tab->t[j];
+        float c[3], tg[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float* P = pos + (a * N) * (kExpandTile + 1) + sl;
+            const float v1 = P[seg * (kExpandTile + 1)], v2 = P[(seg + 1) * (kExpandTile + 1)];
+            const float v0 = seg == 0 ? v1 + (v1 - v2) : P[(seg - 1) * (kExpandTile + 1)];
+            const float v3 = seg + 1 == N - 1 ? v2 + (v2 - v1) : P[(seg + 2) * (kExpandTile + 1)];
+            const float b1 = v1 + (1.0f / 3.0f) * ((v2 - v0) / 2.0f), b2 = v2 - (1.0f / 3.0f) * ((v3 - v1) / 2.0f);
+            const float b01 = mixf(v1, b1, t), b11 = mixf(b1, b2, t), b21 = mixf(b2, v2, t);
+            c[a] = mixf(mixf(b01, b11, t), mixf(b11, b21, t), t);
+            tg[a] = v2 - v1;
+        }
+        const float w = tab->width[j] * tab->wr[k] * tab->sd[form[sl * I + k]][j];
+        const float inv = 1.0f / sqrtf(tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2]);
+        const size_t e = perm ? (size_t)perm[s] : (size_t)s;
+        const size_t o = (e * I + k) * (size_t)(D + 1) + j;
+        pos_width[o] = make_float4(fmaf(w, tab->dirx[k], c[0]), c[1], fmaf(w, tab->dirz[k], c[2]), tab->strand_width[j]);
+        tangent_u[o] = make_float4(tg[0] * inv, tg[1] * inv, tg[2] * inv, tab->u[k]);
+    }
+}
+
 }  // namespace rvh

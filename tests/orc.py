@@ -67,6 +67,7 @@ def lib():
         L.orc_sdf_sample.restype = C.c_int
         L.orc_sdf_bake_colliders.argtypes = [_fp, C.c_int, _ip, _fp, C.c_float, _fp]
         L.orc_sdf_bake_mesh.argtypes = [_fp, _ip, C.c_int, _ip, _fp, C.c_float, _fp]
+        L.orc_expand_strands.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp]
         _lib = L
     return _lib
 
@@ -194,6 +195,16 @@ def sdf_bake_mesh(verts, tris, dim, origin, cell):
     out = np.zeros((d[2], d[1], d[0]), np.float32)
     lib().orc_sdf_bake_mesh(_f(v), t.ctypes.data_as(C.POINTER(C.c_int)), t.shape[0], d.ctypes.data_as(C.POINTER(C.c_int)), _f(o), C.c_float(cell), _f(out))
     return out
+
+
+def expand_strands(strands, isolines=12, divisions=42):
+    """hair.tesc/hair.tese restated: (pos_width, tangent_u), each [S, isolines, divisions+1, 4]."""
+    st = np.ascontiguousarray(strands, np.float32)
+    S, _, N, _ = st.shape
+    pw = np.zeros((S, isolines, divisions + 1, 4), np.float32)
+    tu = np.zeros_like(pw)
+    lib().orc_expand_strands(_f(st), S, N, isolines, divisions, _f(pw), _f(tu))
+    return pw, tu
 
 
 # ---- oracle/_ref: the reference's own sources compiled here ---------------------------

@@ -342,3 +342,59 @@ def test_gpu_fused_gather_equals_stand_alone_gather(flags):
     b.close()
     assert np.abs(fused[:, 0, :, :3] - split[:, 0, :, :3]).max() <= 1e-6
     assert np.abs(fused[:, 1, :, :3] - split[:, 1, :, :3]).max() <= 1e-4
+
+
+# ---- guide strand -> render strands (hair.tesc / hair.tese) -------------------------
+
+def test_oracle_expansion_follows_hair_tese():
+    """Closed-form properties of the restated tessellation-evaluation shader."""
+    S, N = 40, 10
+    st = synth(S, N, 2.5, seed_vel=1)
+    rng = np.random.default_rng(2)
+    st[:, 0, 1:, :3] += rng.normal(scale=0.02, size=(S, N - 1, 3)).astype(np.float32)      # not straight
+    pw, tu = orc.expand_strands(st, 12, 42)
+    assert pw.shape == (S, 12, 43, 4)
+    # isoline coordinate and strand width (hair.tese:313-315)
+    assert np.allclose(tu[..., 3], (np.arange(12) / 12.0)[None, :, None])
+    assert np.allclose(pw[..., 3], 0.02 + (np.arange(43) / 42.0) * (0.01 - 0.02), atol=1e-7)
+    # the sideways deviation is horizontal (dir.y = 0) and vanishes nowhere but is bounded by width * sd_max
+    # => y follows the Bezier curve exactly, and at the segment joints the curve passes through the guide points
+    joints = [(j, j * 9 // 42) for j in range(43) if (j * 9) % 42 == 0]
+    for j, i in joints:
+        assert np.abs(pw[:, :, j, 1] - st[:, 0, i, 1][:, None]).max() < 2e-6
+    # v = 0: sd = 1 (hair.tese:267-269) => offset = width(0) * (rand2 + 0.5) along dir(u), same for every strand
+    off = pw[:, :, 0, :3] - st[:, 0, 0, :3][:, None, :]
+    assert np.abs(off - off[0:1]).max() < 1e-6
+    r = np.linalg.norm(off[0], axis=1)
+    assert np.all(r >= 0.5 * 0.05 * 0.5 - 1e-6) and np.all(r <= 0.5 * 0.05 * 1.5 + 1e-6)
+    ang = np.arctan2(off[0, :, 2], off[0, :, 0]) % (2 * np.pi)
+    assert np.allclose(ang, 2 * np.pi * np.arange(12) / 12.0, atol=1e-4)
+    # unit tangents of the guide's own segments
+    assert np.abs(np.linalg.norm(tu[..., :3], axis=-1) - 1).max() < 1e-6
+    seg = np.minimum((np.arange(43) / np.float32(42.0) * 9).astype(int), 8)
+    d = st[:, 0, seg + 1, :3] - st[:, 0, seg, :3]
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    assert np.abs(tu[:, 0, :, :3] - d).max() < 1e-6
+    # all five deviation profiles and "none" occur across strands x isolines
+    dev = np.linalg.norm(pw[:, :, -1, [0, 2]] - pw[:, :, 21, [0, 2]], axis=-1)
+    assert len(np.unique(np.round(dev / (dev.max() + 1e-9), 2))) > 6
+
+
+@gpu
+@pytest.mark.parametrize("S,N,I,D", [(900, 10, 12, 42), (5000, 32, 12, 42), (1500, 16, 5, 17), (33, 2, 3, 4)])
+def test_gpu_expansion_matches_oracle(S, N, I, D):
+    cols = rvh.scenes.bench_colliders()
+    rest = np.float32(2.5) / np.float32(N - 1)
+    st = synth(S, N, 2.5, seed_vel=5)
+    sim = _sim(S, N, rvh.GRID_ON, rest, cols)
+    sim.upload(st)
+    for k in range(3):
+        sim.step(DT, 0.0)
+    state = sim.download()
+    pw, tu, ms = sim.expand(I, D)
+    sim.close()
+    ref_pw, ref_tu = orc.expand_strands(state, I, D)
+    assert pw.shape == ref_pw.shape == (S, I, D + 1, 4)
+    assert np.abs(pw - ref_pw).max() <= 2e-6 * 4.0          # FMA contraction only: every transcendental is tabulated on the host
+    assert np.abs(tu - ref_tu).max() <= 2e-6
+    assert ms > 0
