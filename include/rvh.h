@@ -121,6 +121,15 @@ int rvh_upload_strands_aos(rvh_ctx* ctx, const void* strands, size_t bytes);
  * as Strand.cpp:166.  Host twin: realtime-vulkan-hair_b200/scenes.py synthetic_head.  Needs rvh_set_colliders first. */
 int rvh_init_synthetic_head(rvh_ctx* ctx, unsigned long long first_strand, float strand_length, unsigned long long seed);
 
+/* GPU scene init from a triangle mesh: follicles drawn on the device with the area weighting
+ * that Strand.cpp:92 leaves as a TODO (triangle from the area CDF, then the reference's folded barycentric sample,
+ * Strand.cpp:96-110), counter-based RNG keyed by first_strand + local index so every rank generates exactly its shard.
+ * tri_pos / tri_nrm = ntris x 3 corners x 3 floats (tri_nrm may be NULL: face normals).  Strands leave the surface at rest
+ * spacing strand_length/(N-1).  Host twin: realtime-vulkan-hair_b200/scenes.py mesh_head.  (The reference's own uniform
+ * srand(8) placement is reproduced bit for bit by the host mirror, rvh_host::Hair.) */
+int rvh_init_from_mesh(rvh_ctx* ctx, const float* tri_pos, const float* tri_nrm, int ntris, unsigned long long first_strand,
+                       float strand_length, unsigned long long seed);
+
 /* ---- head SDF collision (north-star extension; the reference has analytic ellipsoids only) ----------------
  * The volume is a dense float array of signed distances at the NODES of a regular lattice, node (i,j,k) at
  * origin + cell*(i,j,k), stored x-fastest [nz][ny][nx], negative inside.  With RVH_SDF_ON a point x whose lattice

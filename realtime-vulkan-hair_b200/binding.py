@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "rvh_profile_enable", "rvh_profile_read", "rvh_sync", "rvh_last_step_ms", "rvh_kernel_launches",
     "rvh_last_error", "rvh_destroy", "rvh_collider_build", "rvh_collider_translate", "rvh_wind_fbm",
     "rvh_abi_version", "rvh_set_head_sdf", "rvh_bake_head_sdf_from_colliders", "rvh_bake_head_sdf_from_mesh",
-    "rvh_download_head_sdf", "rvh_sdf_mode", "rvh_expand_strands", "rvh_expand_device_buffers",
+    "rvh_download_head_sdf", "rvh_sdf_mode", "rvh_expand_strands", "rvh_expand_device_buffers", "rvh_init_from_mesh",
 ]
 
 
@@ -92,6 +92,7 @@ def load_library():
     L.rvh_download_head_sdf.argtypes = [vp, fp, C.c_size_t]
     L.rvh_sdf_mode.argtypes = [vp]
     L.rvh_expand_strands.argtypes = [vp, C.c_int, C.c_int, fp, fp, C.c_size_t, fp]
+    L.rvh_init_from_mesh.argtypes = [vp, fp, fp, C.c_int, C.c_ulonglong, C.c_float, C.c_ulonglong]
     L.rvh_expand_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     _lib = L
     return L
@@ -185,6 +186,13 @@ class HairSim:
 
     def init_synthetic_head(self, first_strand=0, strand_length=2.5, seed=8):
         self._check(self.L.rvh_init_synthetic_head(self.ctx, first_strand, strand_length, seed), "rvh_init_synthetic_head")
+
+    def init_from_mesh(self, tri_pos, tri_nrm=None, first_strand=0, strand_length=2.5, seed=8):
+        """tri_pos / tri_nrm: float32 [ntris, 3, 3] corner positions / normals (normals optional)."""
+        tp = np.ascontiguousarray(tri_pos, np.float32).reshape(-1, 9)
+        tn = None if tri_nrm is None else np.ascontiguousarray(tri_nrm, np.float32).reshape(-1, 9)
+        self._check(self.L.rvh_init_from_mesh(self.ctx, _fptr(tp), None if tn is None else _fptr(tn), tp.shape[0], first_strand, strand_length, seed),
+                    "rvh_init_from_mesh")
 
     def upload_ptr(self, ptr, nbytes):
         self._check(self.L.rvh_upload_strands_aos(self.ctx, C.c_void_p(ptr), nbytes), "rvh_upload_strands_aos")

@@ -527,6 +527,45 @@ int rvh_init_synthetic_head(rvh_ctx* ctx, unsigned long long first_strand, float
     return unpack_from_staging(ctx);
 }
 
+int rvh_init_from_mesh(rvh_ctx* ctx, const float* tri_pos, const float* tri_nrm, int ntris, unsigned long long first_strand,
+                       float strand_length, unsigned long long seed) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!tri_pos || ntris < 1) return fail(ctx, RVH_ERR_INVALID, "mesh needs >= 1 triangle");
+    if (!(strand_length > 0.f)) return fail(ctx, RVH_ERR_INVALID, "strand_length must be > 0");
+    // area CDF in double, sequential sum, normalised, rounded to float (host twin: scenes.triangle_cdf)
+    std::vector<double> acc(ntris);
+    double total = 0.0;
+    for (int t = 0; t < ntris; ++t) {
+        const float* A = tri_pos + 9 * (size_t)t;
+        const double e1[3] = { (double)A[3] - A[0], (double)A[4] - A[1], (double)A[5] - A[2] }, e2[3] = { (double)A[6] - A[0], (double)A[7] - A[1], (double)A[8] - A[2] };
+        const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+        total += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+        acc[t] = total;
+    }
+    if (!(total > 0.0)) return fail(ctx, RVH_ERR_INVALID, "mesh has zero area");
+    std::vector<float> cdf(ntris);
+    for (int t = 0; t < ntris; ++t) cdf[t] = (float)(acc[t] / total);
+    cdf[ntris - 1] = 1.0f;
+    CU(cudaSetDevice(ctx->cfg.device));
+    float *dpos = nullptr, *dnrm = nullptr, *dcdf = nullptr;
+    CU(cudaMalloc(&dpos, sizeof(float) * 9 * ntris));
+    CU(cudaMalloc(&dcdf, sizeof(float) * ntris));
+    if (tri_nrm) CU(cudaMalloc(&dnrm, sizeof(float) * 9 * ntris));
+    cudaError_t e = cudaMemcpyAsync(dpos, tri_pos, sizeof(float) * 9 * ntris, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dcdf, cdf.data(), sizeof(float) * ntris, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && tri_nrm) e = cudaMemcpyAsync(dnrm, tri_nrm, sizeof(float) * 9 * ntris, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const float rest = strand_length / ((float)ctx->N - 1.0f);
+        k_mesh_follicles_aos<<<(ctx->S + 255) / 256, 256, 0, ctx->stream>>>((float4*)ctx->aos_dev, ctx->S, ctx->N, first_strand, seed, rest, dpos, dnrm, dcdf, ntris);
+        e = cudaGetLastError();
+        ctx->launches += 1;
+    }
+    int r = e == cudaSuccess ? unpack_from_staging(ctx) : fail(ctx, RVH_ERR_CUDA, std::string("rvh_init_from_mesh: ") + cudaGetErrorString(e));
+    cudaStreamSynchronize(ctx->stream);                      // the pageable host arrays and the temporaries are released now
+    cudaFree(dpos); cudaFree(dnrm); cudaFree(dcdf);
+    return r;
+}
+
 int rvh_download_strands_aos(rvh_ctx* ctx, void* strands, size_t bytes) {
     if (!ctx) return RVH_ERR_INVALID;
     if (!strands || bytes != ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "strands must be S*48*N bytes");

@@ -1158,6 +1158,50 @@ k_synth_head_aos(float4* __restrict__ aos, int S, int N, unsigned long long firs
     }
 }
 
+// ---- GPU scene init from a triangle mesh ---------------------------------------------------
+// Follicle placement of Strand.cpp:88-110 on the device, with the fix its own TODO asks for ("account for differences in
+// triangle area", Strand.cpp:92): the triangle is drawn from the area CDF (binary search) instead of uniformly; the
+// barycentric fold (Strand.cpp:100-103) is kept; the normal is the interpolated corner normal (face normal when the mesh
+// has none).  Counter-based splitmix64 keyed by the GLOBAL strand id, three draws per strand, so every rank generates
+// exactly its shard.  Strands leave the surface along normalize(n + 0.1*(0.05, 5, -2)) at exact rest spacing with
+// velocity (0,0,-1) (Strand.cpp:166), like the synthetic head.  Host twin: scenes.mesh_head.
+__global__ void __launch_bounds__(256)
+k_mesh_follicles_aos(float4* __restrict__ aos, int S, int N, unsigned long long first_strand, unsigned long long seed, float rest,
+                     const float* __restrict__ tri_pos, const float* __restrict__ tri_nrm, const float* __restrict__ cdf, int ntris) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const unsigned long long base = (seed << 32) + 3ull * (first_strand + (unsigned long long)s);
+    const float r0 = (float)(splitmix64(base) >> 40) * (1.0f / 16777216.0f);
+    float u = (float)(splitmix64(base + 1ull) >> 40) * (1.0f / 16777216.0f);
+    float v = (float)(splitmix64(base + 2ull) >> 40) * (1.0f / 16777216.0f);
+    int lo = 0, hi = ntris - 1;                               // smallest t with cdf[t] > r0
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(cdf + mid) > r0) hi = mid; else lo = mid + 1; }
+    if (__fadd_rn(u, v) >= 1.0f) { u = __fsub_rn(1.0f, u); v = __fsub_rn(1.0f, v); }
+    const float w = __fsub_rn(__fsub_rn(1.0f, u), v);
+    const float* A = tri_pos + 9 * (size_t)lo;
+    float root[3], n[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) root[a] = __fadd_rn(__fadd_rn(__fmul_rn(A[a], w), __fmul_rn(A[3 + a], u)), __fmul_rn(A[6 + a], v));
+    if (tri_nrm) {
+        const float* Nn = tri_nrm + 9 * (size_t)lo;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) n[a] = __fadd_rn(__fadd_rn(__fmul_rn(Nn[a], w), __fmul_rn(Nn[3 + a], u)), __fmul_rn(Nn[6 + a], v));
+    } else {
+        const float e1[3] = { A[3] - A[0], A[4] - A[1], A[5] - A[2] }, e2[3] = { A[6] - A[0], A[7] - A[1], A[8] - A[2] };
+        n[0] = e1[1] * e2[2] - e1[2] * e2[1]; n[1] = e1[2] * e2[0] - e1[0] * e2[2]; n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+    }
+    const float inl = 1.0f / sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    float dx = n[0] * inl + 0.1f * 0.05f, dy = n[1] * inl + 0.1f * 5.0f, dz = n[2] * inl + 0.1f * -2.0f;
+    const float idl = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= idl; dy *= idl; dz *= idl;
+    float4* cp = aos + (size_t)s * 3 * N;
+    for (int j = 0; j < N; ++j) {
+        const float t = (float)j * rest;
+        cp[j] = make_float4(root[0] + t * dx, root[1] + t * dy, root[2] + t * dz, 1.0f);
+        cp[N + j] = make_float4(0.0f, 0.0f, -1.0f, 0.0f);
+    }
+}
+
 // Morton key (10 bits per axis over the grid box) of each strand's root, for spatial ordering.
 __device__ __forceinline__ unsigned part1by2(unsigned x) {
     x &= 0x3ffu;

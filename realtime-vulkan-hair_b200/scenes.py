@@ -81,6 +81,55 @@ def synthetic_head(num_strands, num_points, strand_length=2.5, first_strand=0, c
     return out
 
 
+def triangle_cdf(tri_pos):
+    """Area CDF of a triangle soup [ntris, 3, 3] as rvh_init_from_mesh builds it: double areas, sequential sum, float32."""
+    t = np.asarray(tri_pos, np.float32).reshape(-1, 3, 3).astype(np.float64)
+    c = np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0])
+    area = 0.5 * np.sqrt(c[:, 0] * c[:, 0] + c[:, 1] * c[:, 1] + c[:, 2] * c[:, 2])
+    acc = np.cumsum(area)
+    cdf = (acc / acc[-1]).astype(np.float32)
+    cdf[-1] = 1.0
+    return cdf
+
+
+def mesh_head(num_strands, num_points, strand_length, tri_pos, tri_nrm=None, first_strand=0, seed=8):
+    """Host twin of rvh_init_from_mesh (k_mesh_follicles_aos): area-weighted follicles on a triangle soup."""
+    tp = np.asarray(tri_pos, np.float32).reshape(-1, 3, 3)
+    cdf = triangle_cdf(tp)
+    S, N = int(num_strands), int(num_points)
+    rest = np.float32(np.float32(strand_length) / np.float32(N - 1))
+    old = np.seterr(over="ignore")
+    try:
+        sid = np.arange(S, dtype=np.uint64) + np.uint64(first_strand)
+        base = (np.uint64(seed) << np.uint64(32)) + np.uint64(3) * sid
+        r = [(_splitmix64(base + np.uint64(k)) >> np.uint64(40)).astype(np.float32) / np.float32(1 << 24) for k in range(3)]
+    finally:
+        np.seterr(**old)
+    tri = np.searchsorted(cdf, r[0], side="right")            # smallest t with cdf[t] > r0
+    tri = np.minimum(tri, len(cdf) - 1)
+    u, v = r[1].copy(), r[2].copy()
+    fold = (u + v) >= np.float32(1.0)
+    u[fold] = np.float32(1.0) - u[fold]
+    v[fold] = np.float32(1.0) - v[fold]
+    w = (np.float32(1.0) - u) - v
+    A, B, Cc = tp[tri, 0], tp[tri, 1], tp[tri, 2]
+    root = (A * w[:, None] + B * u[:, None]) + Cc * v[:, None]
+    if tri_nrm is not None:
+        tn = np.asarray(tri_nrm, np.float32).reshape(-1, 3, 3)
+        n = (tn[tri, 0] * w[:, None] + tn[tri, 1] * u[:, None]) + tn[tri, 2] * v[:, None]
+    else:
+        n = np.cross(B - A, Cc - A).astype(np.float32)
+    n = n / np.linalg.norm(n, axis=1, keepdims=True).astype(np.float32)
+    d = n + np.float32(0.1) * np.array([0.05, 5.0, -2.0], np.float32)
+    d = d / np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    out = np.zeros((S, 3, N, 4), np.float32)
+    j = np.arange(N, dtype=np.float32)
+    out[:, 0, :, :3] = root[:, None, :] + (j * rest)[None, :, None] * d[:, None, :]
+    out[:, 0, :, 3] = 1.0
+    out[:, 1, :, :] = np.array([0.0, 0.0, -1.0, 0.0], np.float32)
+    return out, tri
+
+
 def shard_range(num_strands, rank, nranks):
     """Contiguous strand range [lo, hi) owned by `rank`."""
     lo = (num_strands * rank) // nranks

@@ -398,3 +398,49 @@ def test_gpu_expansion_matches_oracle(S, N, I, D):
     assert np.abs(pw - ref_pw).max() <= 2e-6 * 4.0          # FMA contraction only: every transcendental is tabulated on the host
     assert np.abs(tu - ref_tu).max() <= 2e-6
     assert ms > 0
+
+
+# ---- GPU follicle placement on a mesh, area weighted (Strand.cpp:92 TODO) ----------------
+
+def scalp_soup():
+    """The reference's follicle surface (models/mannequin_segment.obj, frozen as arrays under tests/golden/): quads -> triangle soup."""
+    import os
+    m = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mannequin_segment_mesh.npz"))
+    fv, fn = m["fv"], m["fn"]
+    idx = np.concatenate([fv[:, [0, 1, 2]], fv[:, [0, 2, 3]]])
+    nidx = np.concatenate([fn[:, [0, 1, 2]], fn[:, [0, 2, 3]]])
+    return m["v"][idx].astype(np.float32), m["vn"][nidx].astype(np.float32)
+
+
+def test_host_mesh_follicles_are_area_weighted_and_on_the_surface():
+    tp, tn = scalp_soup()
+    S = 200000
+    st, tri = rvh.scenes.mesh_head(S, 4, 0.3, tp, tn)
+    area = 0.5 * np.linalg.norm(np.cross(tp[:, 1] - tp[:, 0], tp[:, 2] - tp[:, 0]), axis=1)
+    want = area / area.sum() * S
+    got = np.bincount(tri, minlength=len(tp))
+    big = want > 50
+    assert np.abs(got[big] - want[big]).max() < 6 * np.sqrt(want[big]).max()            # Poisson scatter, not uniform-per-triangle
+    assert np.corrcoef(got, want)[0, 1] > 0.95
+    # roots lie in their triangle's plane
+    nrm = np.cross(tp[:, 1] - tp[:, 0], tp[:, 2] - tp[:, 0])
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    off = np.einsum("ij,ij->i", st[:, 0, 0, :3] - tp[tri, 0], nrm[tri])
+    assert np.abs(off).max() < 1e-5
+    # shards reproduce the global sequence
+    part, _ = rvh.scenes.mesh_head(1000, 4, 0.3, tp, tn, first_strand=5000)
+    assert np.array_equal(part, st[5000:6000])
+
+
+@gpu
+def test_gpu_mesh_follicles_match_host_twin():
+    tp, tn = scalp_soup()
+    S, N, L = 20000, 12, 1.0
+    for first, normals in ((0, tn), (777, None)):
+        sim = _sim(S, N, 0, np.float32(L) / np.float32(N - 1), rvh.scenes.bench_colliders())
+        sim.init_from_mesh(tp, normals, first_strand=first, strand_length=L, seed=8)
+        got = sim.download()
+        sim.close()
+        want, _ = rvh.scenes.mesh_head(S, N, L, tp, normals, first_strand=first, seed=8)
+        assert np.abs(got[:, 0, :, :3] - want[:, 0, :, :3]).max() <= 4e-6 * 4.0
+        assert np.array_equal(got[:, 1], want[:, 1]) and np.all(got[:, 2] == 0) and np.all(got[:, 0, :, 3] == 1)
