@@ -234,7 +234,10 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
                 int chunks = std::max(1, std::min(rows, (ctx->splat_target_warps + warps - 1) / warps));
                 const int rpc = (rows + chunks - 1) / chunks;
                 chunks = (rows + rpc - 1) / rpc;
-                k_grid_splat<<<dim3(ctx->S_pad / kSplatThreads, chunks), kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid, rpc);
+                if (ctx->P.scale > 0.f && ctx->P.scale < 8388608.0f)
+                    k_grid_splat<true><<<dim3(ctx->S_pad / kSplatThreads, chunks), kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid, rpc);
+                else
+                    k_grid_splat<false><<<dim3(ctx->S_pad / kSplatThreads, chunks), kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid, rpc);
             }
             else k_grid_splat_redux<<<ctx->S_pad / kSplatThreads, kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid);
             prof_end(ctx);
@@ -736,7 +739,7 @@ int rvh_expand_strands(rvh_ctx* ctx, int isolines, int divisions, float* pos_wid
         CU(cudaMalloc(&ctx->exp_tu, verts * sizeof(float4)));
         ctx->exp_cap = verts;
     }
-    const size_t sm = (size_t)3 * ctx->N * (kExpandTile + 1) * sizeof(float) + (size_t)kExpandTile * isolines;
+    const size_t sm = ((size_t)3 * ctx->N * (kExpandTile + 1) + 10 * (divisions + 1) + 4 * isolines + (size_t)isolines * (divisions + 1) + kExpandTile) * sizeof(float) + (size_t)kExpandTile * isolines;
     CU(cudaFuncSetAttribute(k_expand_strands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const bool reorder = ctx->perm != nullptr && !(ctx->cfg.flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
     if (ms_out) CU(cudaEventRecord(ctx->ev_a, ctx->stream));

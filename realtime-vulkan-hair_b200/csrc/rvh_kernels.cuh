@@ -726,6 +726,7 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
 #ifndef RVH_SPLAT_THREADS
 #define RVH_SPLAT_THREADS 128
 #endif
+
 constexpr int kSplatThreads = RVH_SPLAT_THREADS;
 constexpr float kSplatAggVmax = 60.0f;    // |c| <= 6e7 per contribution, 8 per lane, 4 lanes per corner: < 2^31
 constexpr int kStageW = 40;                // words between the a=0 and a=1 weight rows: distinct banks for LDS.64
@@ -759,6 +760,9 @@ __device__ __forceinline__ void splat_flush_cell(const StepParams& P, unsigned l
 
 // Rows are independent in the splat (unlike the FTL chain), so blockIdx.y splits them into chunks of
 // `rows_per_chunk`: scenes with few strands (C3: 100K x 64 = 3,125 warps walking 63 rows) still fill the machine.
+// MAGIC (host: grid_scale < 2^23): the density term 0 <= SCALE*w < 2^23 is truncated by FADD.RZ with 2^23 on the FMA pipe
+// instead of F2I on the quarter-rate XU pipe (same integer; splat 0.478 -> 0.460 ms at 1M x 32).
+template <bool MAGIC>
 __global__ void __launch_bounds__(kSplatThreads)
 k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid, int rows_per_chunk) {
     constexpr unsigned kFull = 0xffffffffu;
@@ -829,8 +833,12 @@ k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ pla
             const float2 cd = __fmul2_rn(sc2, tw);
             const int2 k = kp[i2];
             // key -1 points may carry garbage weights: they match neither K0 nor K1 (both != -1 when used)
-            const int ix0 = __float2int_rz(cx.x), iy0 = __float2int_rz(cy.x), iz0 = __float2int_rz(cz.x), id0 = __float2int_rz(cd.x);
-            const int ix1 = __float2int_rz(cx.y), iy1 = __float2int_rz(cy.y), iz1 = __float2int_rz(cz.y), id1 = __float2int_rz(cd.y);
+            const int ix0 = __float2int_rz(cx.x), iy0 = __float2int_rz(cy.x), iz0 = __float2int_rz(cz.x);
+            const int ix1 = __float2int_rz(cx.y), iy1 = __float2int_rz(cy.y), iz1 = __float2int_rz(cz.y);
+            int id0, id1;
+            if (MAGIC) {
+                id0 = __float_as_int(__fadd_rz(cd.x, 8388608.0f)) - 0x4B000000; id1 = __float_as_int(__fadd_rz(cd.y, 8388608.0f)) - 0x4B000000;
+            } else { id0 = __float2int_rz(cd.x); id1 = __float2int_rz(cd.y); }
             if (k.x == K0) { a0 += ix0; a1 += iy0; a2 += iz0; a3 += id0; }
             if (k.y == K0) { a0 += ix1; a1 += iy1; a2 += iz1; a3 += id1; }
             if (K1 != -1) {
@@ -1382,46 +1390,64 @@ __device__ __forceinline__ float mixf(float a, float b, float t) { return fmaf(t
 __global__ void __launch_bounds__(256)
 k_expand_strands(const float* __restrict__ planes, const int* __restrict__ perm, const ExpandTables* __restrict__ tab,
                  float4* __restrict__ pos_width, float4* __restrict__ tangent_u, int S, int S_pad, int N, int I, int D) {
+    // shared: guide positions of the tile, the per-(strand, isoline) deviation profile, and every table the vertex loop
+    // reads (the loop is issue-bound: no integer division, no global table loads inside it)
     extern __shared__ float esm[];
+    const int D1 = D + 1, per = I * D1;
     float* pos = esm;                                        // [3][N][kExpandTile + 1]
-    unsigned char* form = reinterpret_cast<unsigned char*>(pos + 3 * N * (kExpandTile + 1));   // [kExpandTile][I]
+    float* tj = pos + 3 * N * (kExpandTile + 1);             // [4][D1]: t, width, strand_width, (int) seg
+    float* sd = tj + 4 * D1;                                 // [6][D1]
+    float* tk = sd + 6 * D1;                                 // [4][I]: u, dirx, dirz, wr
+    int* kj = reinterpret_cast<int*>(tk + 4 * I);            // [per]: k << 16 | j of flat vertex q
+    int* eidx = kj + per;                                    // [kExpandTile]: external strand index
+    unsigned char* form = reinterpret_cast<unsigned char*>(eidx + kExpandTile);   // [kExpandTile][I]
     const int s0 = blockIdx.x * kExpandTile;
+    if (threadIdx.x < kExpandTile) { const int s = s0 + threadIdx.x; eidx[threadIdx.x] = (perm && s < S) ? perm[s] : s; }
     for (int q = threadIdx.x; q < 3 * N * kExpandTile; q += blockDim.x) {
         const int sl = q % kExpandTile, r = q / kExpandTile;      // r = k*N + row
         const int k = r / N, row = r % N;
         pos[r * (kExpandTile + 1) + sl] = (s0 + sl < S_pad) ? planes[tiled_index(6, S_pad, row, k, s0 + sl)] : 0.f;
     }
+    for (int j = threadIdx.x; j < D1; j += blockDim.x) {
+        tj[j] = tab->t[j]; tj[D1 + j] = tab->width[j]; tj[2 * D1 + j] = tab->strand_width[j]; tj[3 * D1 + j] = __int_as_float(tab->seg[j]);
+#pragma unroll
+        for (int f = 0; f < 6; ++f) sd[f * D1 + j] = tab->sd[f][j];
+    }
+    for (int k = threadIdx.x; k < I; k += blockDim.x) { tk[k] = tab->u[k]; tk[I + k] = tab->dirx[k]; tk[2 * I + k] = tab->dirz[k]; tk[3 * I + k] = tab->wr[k]; }
+    for (int q = threadIdx.x; q < per; q += blockDim.x) kj[q] = ((q / D1) << 16) | (q % D1);
     __syncthreads();
     for (int q = threadIdx.x; q < kExpandTile * I; q += blockDim.x) {
         const int sl = q / I, k = q % I;
-        form[q] = (unsigned char)expand_form(tab->u[k], pos[(0 * N) * (kExpandTile + 1) + sl], pos[(1 * N) * (kExpandTile + 1) + sl], pos[(2 * N) * (kExpandTile + 1) + sl]);
+        form[q] = (unsigned char)expand_form(tk[k], pos[(0 * N) * (kExpandTile + 1) + sl], pos[(1 * N) * (kExpandTile + 1) + sl], pos[(2 * N) * (kExpandTile + 1) + sl]);
     }
     __syncthreads();
-    const int per = I * (D + 1);
-    for (int q = threadIdx.x; q < kExpandTile * per; q += blockDim.x) {
-        const int sl = q / per, rem = q - sl * per, k = rem / (D + 1), j = rem - k * (D + 1);
-        const int s = s0 + sl;
-        if (s >= S) continue;
-        const int seg = tab->seg[j];
-        const float t = tab->t[j];
+    constexpr int RS = kExpandTile + 1;
+    // flat walk over the tile's kExpandTile * per vertices, (strand, vertex) kept incrementally
+    int sl = 0, q = threadIdx.x;
+    while (q >= per) { q -= per; ++sl; }
+    while (sl < kExpandTile && s0 + sl < S) {
+        const int kq = kj[q], k = kq >> 16, j = kq & 0xffff;
+        const int seg = __float_as_int(tj[3 * D1 + j]);
+        const float t = tj[j];
         float c[3], tg[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float* P = pos + (a * N) * (kExpandTile + 1) + sl;
-            const float v1 = P[seg * (kExpandTile + 1)], v2 = P[(seg + 1) * (kExpandTile + 1)];
-            const float v0 = seg == 0 ? v1 + (v1 - v2) : P[(seg - 1) * (kExpandTile + 1)];
-            const float v3 = seg + 1 == N - 1 ? v2 + (v2 - v1) : P[(seg + 2) * (kExpandTile + 1)];
+            const float* P = pos + (a * N + seg) * RS + sl;
+            const float v1 = P[0], v2 = P[RS];
+            const float v0 = seg == 0 ? v1 + (v1 - v2) : P[-RS];
+            const float v3 = seg + 1 == N - 1 ? v2 + (v2 - v1) : P[2 * RS];
             const float b1 = v1 + (1.0f / 3.0f) * ((v2 - v0) / 2.0f), b2 = v2 - (1.0f / 3.0f) * ((v3 - v1) / 2.0f);
             const float b01 = mixf(v1, b1, t), b11 = mixf(b1, b2, t), b21 = mixf(b2, v2, t);
             c[a] = mixf(mixf(b01, b11, t), mixf(b11, b21, t), t);
             tg[a] = v2 - v1;
         }
-        const float w = tab->width[j] * tab->wr[k] * tab->sd[form[sl * I + k]][j];
+        const float w = tj[D1 + j] * tk[3 * I + k] * sd[form[sl * I + k] * D1 + j];
         const float inv = 1.0f / sqrtf(tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2]);
-        const size_t e = perm ? (size_t)perm[s] : (size_t)s;
-        const size_t o = (e * I + k) * (size_t)(D + 1) + j;
-        pos_width[o] = make_float4(fmaf(w, tab->dirx[k], c[0]), c[1], fmaf(w, tab->dirz[k], c[2]), tab->strand_width[j]);
-        tangent_u[o] = make_float4(tg[0] * inv, tg[1] * inv, tg[2] * inv, tab->u[k]);
+        const size_t o = (size_t)eidx[sl] * per + q;         // the strand's vertices are contiguous
+        pos_width[o] = make_float4(fmaf(w, tk[I + k], c[0]), c[1], fmaf(w, tk[2 * I + k], c[2]), tj[2 * D1 + j]);
+        tangent_u[o] = make_float4(tg[0] * inv, tg[1] * inv, tg[2] * inv, tk[k]);
+        q += blockDim.x;
+        while (q >= per) { q -= per; ++sl; }
     }
 }
 

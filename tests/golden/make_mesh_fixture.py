@@ -15,9 +15,29 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OBJ = "/root/reference/src/models/mannequin_segment.obj"
+HEAD_OBJ = "/root/reference/src/models/mannequin.obj"      # the rendered mannequin (main.cpp:222-223): head-SDF bake fixture
+
+
+def head_mesh():
+    """mannequin_head_mesh.npz: v [nv,3] float32, tri [nt,3] int32 (quads split 0-1-2 / 0-2-3), positions only."""
+    v, tri = [], []
+    for ln in open(HEAD_OBJ):
+        t = ln.split()
+        if not t:
+            continue
+        if t[0] == "v":
+            v.append([float(x) for x in t[1:4]])
+        elif t[0] == "f":
+            a = [int(tok.split("/")[0]) - 1 for tok in t[1:]]
+            for k in range(1, len(a) - 1):
+                tri.append([a[0], a[k], a[k + 1]])
+    out = os.path.join(HERE, "mannequin_head_mesh.npz")
+    np.savez_compressed(out, v=np.array(v, np.float32), tri=np.array(tri, np.int32))
+    print(out, os.path.getsize(out), len(v), len(tri))
 
 
 def main():
+    head_mesh()
     v, vn, fv, fn = [], [], [], []
     for ln in open(OBJ):
         t = ln.split()

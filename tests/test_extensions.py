@@ -444,3 +444,65 @@ def test_gpu_mesh_follicles_match_host_twin():
         want, _ = rvh.scenes.mesh_head(S, N, L, tp, normals, first_strand=first, seed=8)
         assert np.abs(got[:, 0, :, :3] - want[:, 0, :, :3]).max() <= 4e-6 * 4.0
         assert np.array_equal(got[:, 1], want[:, 1]) and np.all(got[:, 2] == 0) and np.all(got[:, 0, :, 3] == 1)
+
+
+# ---- the real head: SDF baked from the mannequin mesh (reference asset models/mannequin.obj, main.cpp:222-223) ----
+
+def head_mesh():
+    import os
+    m = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mannequin_head_mesh.npz"))
+    return (m["v"] * np.float32(0.98)).astype(np.float32), m["tri"]          # rendered with glm::scale(0.98), main.cpp:223
+
+
+HEAD_LATTICE = ([30, 55, 24], np.array([-1.45, -1.6, -1.15], np.float32), np.float32(0.1))
+
+
+def test_oracle_head_mesh_bake_is_a_plausible_signed_distance():
+    verts, tris = head_mesh()
+    dim, origin, cell = HEAD_LATTICE
+    vol = orc.sdf_bake_mesh(verts, tris, dim, origin, cell)
+    assert np.isfinite(vol).all()
+    inside = vol < 0
+    assert 0.08 < inside.mean() < 0.5                              # the head, neck and bust fill part of the box
+    # the centre of the head ellipsoid of the shipped scene (main.cpp:231) is inside, a corner of the box is outside
+    c = np.round((np.array([0.0, 2.64, 0.08], np.float32) - origin) / cell).astype(int)
+    assert vol[c[2], c[1], c[0]] < -0.3
+    assert vol[0, 0, 0] > 0.3 and vol[-1, -1, -1] > 0.1
+    # |grad d| ~ 1 away from the medial axis: central differences over the lattice
+    g = np.stack(np.gradient(vol, float(cell)), -1)
+    gn = np.linalg.norm(g, axis=-1)
+    assert 0.8 < np.median(gn) < 1.1
+
+
+@gpu
+def test_gpu_head_mesh_bake_and_step_match_oracle():
+    verts, tris = head_mesh()
+    dim, origin, cell = HEAD_LATTICE
+    want = orc.sdf_bake_mesh(verts, tris, dim, origin, cell)
+    S, N, L = 8000, 24, 2.5
+    cols = rvh.scenes.bench_colliders()
+    rest = np.float32(L) / np.float32(N - 1)
+    sim = _sim(S, N, rvh.SDF_ON | rvh.GRID_ON, rest, cols)
+    sim.bake_head_sdf_from_mesh(verts, tris, dim, origin, cell)
+    got = sim.download_head_sdf()
+    same = np.sign(got) == np.sign(want)
+    assert np.abs(np.abs(got) - np.abs(want)).max() < 2e-5
+    assert same.mean() > 0.999 and np.abs(want[~same]).max(initial=0.0) < 2e-3
+    # one step against the oracle, both sampling the GPU-baked volume
+    p = orc.default_params(S, N, orc.SDF_ON | orc.GRID_ON, rest_length=rest)
+    orc.set_head_sdf(got, origin, cell)
+    try:
+        state = synth(S, N, L, seed_vel=4)
+        for k in range(15):
+            state, _ = orc.step(p, cols, DT, 0.0, state, threads=8)
+        probe = state[::5, 0, 1:, :3].reshape(-1, 3)[:3000]
+        assert sum(1 for ok, d, _ in (orc.sdf_sample(q) for q in probe) if ok and d < 0) > 10
+        ref, _ = orc.step(p, cols, DT, 0.0, state, threads=8)
+        sim.upload(state)
+        sim.step(DT, 0.0)
+        out = sim.download()
+        assert np.abs(out[:, 0, :, :3] - ref[:, 0, :, :3]).max() <= 1e-4 * L
+        assert np.abs(out[:, 1, :, :3] - ref[:, 1, :, :3]).max() <= 1e-4 * L / float(DT)
+    finally:
+        orc.set_head_sdf(None, None, 0)
+        sim.close()
