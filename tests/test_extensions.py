@@ -506,3 +506,61 @@ def test_gpu_head_mesh_bake_and_step_match_oracle():
     finally:
         orc.set_head_sdf(None, None, 0)
         sim.close()
+
+
+# ---- frozen vectors of the extension modes (tests/golden/make_extension_golden.py) -------------------------------
+
+def _golden_ext():
+    import os
+    from conftest import full_state
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extensions.npz")))
+    g["sdf"] = orc.sdf_bake_colliders(g["colliders"], g["sdf_dim"], g["sdf_origin"], g["sdf_cell"])      # re-baked; pinned by slice + sum
+    return g, full_state(g["pre"])
+
+
+GOLDEN_MODES = [("post_sdf", orc.SDF_ON | orc.GRID_ON), ("post_rep", orc.GRID_ON | orc.REPULSION_ON), ("post_both", orc.SDF_ON | orc.GRID_ON | orc.REPULSION_ON)]
+
+
+def test_oracle_extension_modes_reproduce_the_frozen_vectors():
+    g, pre = _golden_ext()
+    S, _, N, _ = pre.shape
+    rest = np.float32(2.5) / np.float32(N - 1)
+    assert np.abs(g["sdf"][int(g["sdf_dim"][2]) // 2] - g["sdf_slice"]).max() <= 1e-6
+    assert abs(float(g["sdf"].astype(np.float64).sum()) - float(g["sdf_sum"])) <= 1e-3
+    orc.set_head_sdf(g["sdf"], g["sdf_origin"], g["sdf_cell"])
+    try:
+        for name, fl in GOLDEN_MODES:
+            out, _ = orc.step(orc.default_params(S, N, fl, rest_length=rest), g["colliders"], DT, 0.0, pre)
+            assert np.abs(out[:, 0:2, :, :3] - g[name]).max() <= 1e-6, name       # same libm => normally bit-identical
+        assert np.abs(g["post_sdf"] - g["post_rep"]).max() > 1e-3                # the modes really differ
+    finally:
+        orc.set_head_sdf(None, None, 0)
+    pw, tu = orc.expand_strands(pre, 4, 9)
+    assert np.abs(pw - g["exp_pw"]).max() <= 1e-6 and np.abs(tu - g["exp_tu"]).max() <= 1e-6
+
+
+@gpu
+def test_gpu_extension_modes_against_the_frozen_vectors():
+    g, pre = _golden_ext()
+    S, _, N, _ = pre.shape
+    L = 2.5
+    rest = np.float32(L) / np.float32(N - 1)
+    for name, fl in GOLDEN_MODES:
+        flags = (rvh.SDF_ON if fl & orc.SDF_ON else 0) | (rvh.GRID_ON if fl & orc.GRID_ON else 0) | (rvh.REPULSION_ON if fl & orc.REPULSION_ON else 0)
+        sim = _sim(S, N, flags, rest, g["colliders"])
+        if flags & rvh.SDF_ON:
+            sim.set_head_sdf(g["sdf"], g["sdf_origin"], float(g["sdf_cell"]))
+        sim.upload(pre)
+        sim.step(DT, 0.0)
+        out = sim.download()
+        if name == "post_sdf":
+            pw, tu, _ = sim.expand(4, 9)          # expansion reads positions only; compare on a fresh upload below
+        sim.close()
+        assert np.abs(out[:, 0, :, :3] - g[name][:, 0]).max() <= 1e-4 * L, name
+        if not (fl & orc.REPULSION_ON):            # repulsion is discontinuous across cell faces (see the repulsion test)
+            assert np.abs(out[:, 1, :, :3] - g[name][:, 1]).max() <= 1e-4 * L / float(DT), name
+    sim = _sim(S, N, 0, rest, g["colliders"])
+    sim.upload(pre)
+    pw, tu, _ = sim.expand(4, 9)
+    sim.close()
+    assert np.abs(pw - g["exp_pw"]).max() <= 8e-6 and np.abs(tu - g["exp_tu"]).max() <= 2e-6
