@@ -26,7 +26,10 @@
 namespace rvh {
 
 constexpr int kMaxEllipsoids = 7;       // colliders 1..7; collider 0 is the sphere
-constexpr int kBlock = 128;
+#ifndef RVH_K1_THREADS
+#define RVH_K1_THREADS 128
+#endif
+constexpr int kBlock = RVH_K1_THREADS;
 constexpr int kTileStrands = 256;       // strands per layout tile; S_pad is a multiple of it
 
 // element index of (row, plane k of NP, strand s) in a tiled array [N][S_pad/256][NP][256]
@@ -583,7 +586,7 @@ template <int V> __device__ __forceinline__ void store_packs(float* __restrict__
 #define RVH_K1_MINBLOCKS 6      // <= 85 registers: 6 CTAs/SM measured fastest on B200 (5: 0.365 ms, 6: 0.357 ms, 7: 0.416 ms at 1M x 32)
 #endif
 #ifndef RVH_K1G_MINBLOCKS
-#define RVH_K1G_MINBLOCKS 5     // with the fused gather: 6 CTAs/SM spill into the loop (0.417 ms), 5: 0.362 ms, 4: 0.369 ms
+#define RVH_K1G_MINBLOCKS 6     // with the fused gather (1M x 32, all on): 4 CTAs/SM 0.383 ms, 5: 0.363 ms, 6 (<= 85 registers, a few spills): 0.356 ms
 #endif
 #ifndef RVH_K1X_MINBLOCKS
 #define RVH_K1X_MINBLOCKS 4     // extension variants (SDF and/or repulsion): more live state
