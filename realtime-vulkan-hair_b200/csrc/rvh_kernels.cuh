@@ -296,6 +296,31 @@ __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* _
     }
 }
 
+// Optional (RVH_K1_PREFETCH=1, off by default): L1 prefetch of the cells gather_pack is about to read, issued at the top of a
+// row, with the gather itself moved behind the collision tests so that their work hides the L2 latency.  Measured on
+// B200 at 1M x 32 (k_ftl_step with fused gather): gather first, no prefetch 0.356 ms; prefetch + late gather 0.481 ms at
+// 6 CTAs/SM, 0.417 ms at 5 -- the velocities stay live across the collision code and the extra spills cost more than
+// the latency they hide.  Unrolling the row loop by 2 (RVH_K1_UNROLL) to ping-pong the prefetch registers: 0.416 ms.
+#ifndef RVH_K1_PREFETCH
+#define RVH_K1_PREFETCH 0
+#endif
+template <class T>
+__device__ __forceinline__ void gather_prefetch(const StepParams& P, const float4* __restrict__ fgrid, T px, T py, T pz) {
+    constexpr int n = VecTraits<T>::n;
+    const AxisCells<T> X = axis_cells<T, false>(P, px, 0), Y = axis_cells<T, false>(P, py, 1), Z = axis_cells<T, false>(P, pz, 2);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        if (cell_ok(X.f[i], P.G - 1) && cell_ok(Y.f[i], P.G - 1) && cell_ok(Z.f[i], P.G - 1)) {
+            const float4* b = fgrid + (X.f[i] + (Y.f[i] + Z.f[i] * P.G) * P.G);
+            const int sy = P.G, sz = P.G * P.G;
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(b));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(b + sy));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(b + sz));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(b + sz + sy));
+        }
+    }
+}
+
 // ---- head SDF sampling (north-star extension; oracle twin: oracle.c sdf_cell / sdf_trilinear) -------------
 // Lattice coordinate u = (p - origin) * inv_cell per axis; the point is "in the volume" when all 8 nodes of its
 // cell exist.  d = trilinear interpolation, x then y then z, each lerp = fma(t, b - a, a): the same operations in
@@ -451,10 +476,14 @@ __device__ __forceinline__ void collision_force(const StepParams& P, const SdfTi
 
 // NELL >= 0: number of ellipsoids known at compile time; NELL == -1: run-time count; NELL <= -2: the head SDF replaces
 // the ellipsoids (-2 plain loads, -3 TMA-staged tile in `tile`).
-template <class T, bool WIND, int NELL>
-__device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const SdfTile& tile, T cx, T cy, T cz, T vx, T vy, T vz,
-                                                    T parx, T pary, T parz) {
+// GATHER != 0: the previous step's gather (+ repulsion when 2) is applied to (vx,vy,vz) right before they are first used,
+// i.e. AFTER the collision tests, whose work hides the latency of the cells prefetched at the top.
+template <class T, bool WIND, int NELL, int GATHER>
+__device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const SdfTile& tile, const float4* __restrict__ fgrid,
+                                                    T cx, T cy, T cz, T vx, T vy, T vz, T parx, T pary, T parz) {
     constexpr int n = VecTraits<T>::n;
+    if (GATHER && RVH_K1_PREFETCH) gather_prefetch<T>(P, fgrid, cx, cy, cz);
+    if (GATHER && !RVH_K1_PREFETCH) gather_pack<T, GATHER == 2>(P, fgrid, cx, cy, cz, vx, vy, vz);
     T fx = bc<T>(0.0f), fy = bc<T>(P.gravity_y), fz = bc<T>(0.0f);       // :150
     if (WIND) {
         const T a1 = vmul(cy, bc<T>(10.0f));
@@ -521,6 +550,7 @@ __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const S
         fx = vadd(fx, ax); fy = vadd(fy, ay); fz = vadd(fz, az);
     }
 
+    if (GATHER && RVH_K1_PREFETCH) gather_pack<T, GATHER == 2>(P, fgrid, cx, cy, cz, vx, vy, vz);
     PointOut<T> o;
     const T dt = bc<T>(P.dt), dt2 = bc<T>(P.dt2);
     const T prx = vfma(dt2, fx, vfma(dt, vx, cx));                      // :187
@@ -588,6 +618,10 @@ template <int V> __device__ __forceinline__ void store_packs(float* __restrict__
 #ifndef RVH_K1G_MINBLOCKS
 #define RVH_K1G_MINBLOCKS 6     // with the fused gather (1M x 32, all on): 4 CTAs/SM 0.383 ms, 5: 0.363 ms, 6 (<= 85 registers, a few spills): 0.356 ms
 #endif
+#ifndef RVH_K1_UNROLL
+#define RVH_K1_UNROLL 1
+#endif
+constexpr int kK1Unroll = RVH_K1_UNROLL;     // row-loop unrolling (2 lets the compiler ping-pong the prefetch registers instead of copying them)
 #ifndef RVH_K1X_MINBLOCKS
 #define RVH_K1X_MINBLOCKS 4     // extension variants (SDF and/or repulsion): more live state
 #endif
@@ -663,6 +697,7 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
     const T minus_inv_dt = bc<T>(-P.inv_dt);
 
     float* prevp = base;
+#pragma unroll kK1Unroll
     for (int i = 1; i < P.N; ++i) {
         float* const curp = nextp;
         nextp += RS;
@@ -691,8 +726,7 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
         T fvx[NP], fvy[NP], fvz[NP], odx[NP], ody[NP], odz[NP];
 #pragma unroll
         for (int u = 0; u < NP; ++u) {
-            if (GATHER) gather_pack<T, GATHER == 2>(P, fgrid, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u]);
-            const PointOut<T> o = point_update<T, WIND, NELL>(P, tile, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
+            const PointOut<T> o = point_update<T, WIND, NELL, GATHER>(P, tile, fgrid, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
             parx[u] = o.px; pary[u] = o.py; parz[u] = o.pz;
             odx[u] = o.dx; ody[u] = o.dy; odz[u] = o.dz;
             // finalise point i-1: v_{i-1} -= d_i / dt   (compute.comp:213-215)
