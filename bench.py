@@ -37,6 +37,9 @@ WORKLOADS = {
     "ns_full": (1 << 20, 32, 2.5, "grid+windB", "1M strands x 32 points per GPU: gravity + wind B + sphere & 5 ellipsoid colliders + voxel-grid friction (int64 grid 64^3)"),
     # north-star "integrate+FTL+collision" target (no hair-hair)
     "ns_nogrid": (1 << 20, 32, 2.5, "windB", "1M strands x 32 points per GPU: gravity + wind B + sphere & 5 ellipsoid colliders, no hair-hair grid"),
+    # BASELINE.json configs[0]: the reference's own scene (main.cpp:226-237), 900 guides x 10 points from mannequin_segment.obj
+    # follicles (srand(8)), frozen in tests/golden/c1_reference_scene.npz by the reference's own Hair::Hair
+    "c1": (900, 10, 2.5, "grid", "C1: the shipped scene, 900 strands x 10 points (Hair::Hair follicles, reference colliders, grid friction as the shader always runs it); 432 KB of state: L2-resident, launch-bound"),
     "c2": (16384, 32, 2.5, "windB", "C2: 16K strands x 32 points, gravity + wind + colliders, no hair-hair (L2-resident, launch-bound)"),
     "c3": (100000, 64, 2.5, "grid", "C3: 100K strands x 64 points, colliders + voxel-grid friction"),
     "c4": (1000000, 16, 0.4, "grid", "C4: 1M fur strands x 16 points per GPU, voxel-grid friction"),
@@ -136,6 +139,12 @@ class ClockSampler:
 
 # ---- the reference on the host cores ----------------------------------------------------------------------
 
+def c1_scene():
+    """(state0 [900,3,10,4], colliders [6,48]) of the shipped scene, as the reference's own constructors produced them."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_reference_scene.npz"))
+    return np.ascontiguousarray(g["state0"], np.float32), np.ascontiguousarray(g["colliders"], np.float32)
+
+
 def _ref_tag(N, flags_s):
     import orc
     tag = "N%d%s" % (N, "_windB" if "windB" in flags_s else ("_windA" if "windA" in flags_s else ""))
@@ -167,6 +176,20 @@ def time_reference(workload, flags_s, steps, warmup, strands_per_proc=8192):
     tag = _ref_tag(N, flags_s) if abs(L - 2.5) < 1e-6 else None      # the shader hard-codes strand length 2.5 (compute.comp:139)
     if "sdf" in flags_s or "rep" in flags_s:
         tag = None                                                   # extensions do not exist in the shader: only the C port has them
+    if workload == "c1" and tag is not None:
+        # the whole workload is 900 strands: one dispatch of the reference shader text per step, one core, exactly as shipped
+        st, cols = c1_scene()
+        for w in range(warmup):
+            st, _, _ = orc.ref_dispatch(tag, st, cols, DT, DT * w)
+        reps = 20
+        t0 = time.perf_counter()
+        for k in range(steps * reps):
+            st, _, _ = orc.ref_dispatch(tag, st, cols, DT, DT * (warmup + k))
+        el = (time.perf_counter() - t0) / reps
+        info = {"kind": "reference", "cores": 1,
+                "sample": "the full workload: 900 strands x 10 points per step, %d x %d steps: the reference's compute.comp text compiled as C++ against its vendored glm "
+                          "(oracle/_ref/libref_compute_%s.so), one dispatch per step on one core, -O2" % (steps, reps, tag)}
+        return 900 * N * steps / el, el, info
     if tag is not None:
         # the shader TU keeps its buffers in globals, so each core runs its own process over its own strand range; the
         # grid is per process (as if the head were dispatched in `cores` independent pieces): same arithmetic per point
@@ -289,12 +312,20 @@ def main():
     grid_on = bool(flags & rvh.GRID_ON)
     rest = float(np.float32(L) / np.float32(N - 1))
     cols = rvh.scenes.bench_colliders()
+    c1 = args.workload == "c1"
+    if c1:
+        if world > 1 and args.scaling != "strong":
+            raise SystemExit("c1 is one fixed scene of 900 strands: use --scaling strong to shard it")
+        c1_state, cols = c1_scene()
+        device_init = False
 
     # synthetic inputs in pinned host memory (global strand ids => every rank makes its own shard)
     aos_bytes = S * 48 * N
     pinned = torch.empty(aos_bytes // 4, dtype=torch.float32, pin_memory=True)
     host = pinned.numpy().reshape(S, 3, N, 4)
-    if not device_init:
+    if c1:
+        host[:] = c1_state[first_strand:first_strand + S]
+    elif not device_init:
         rvh.scenes.synthetic_head(S, N, L, first_strand=first_strand, colliders=cols, out=host)
 
     cfg = rvh.default_config(S, N, flags=flags, device=local, rest_length=rest, strands_per_thread=args.spt)
@@ -429,7 +460,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "strands_per_gpu": S, "strands_total": S_total, "points_per_strand": N,
-                   "scene_init": "GPU (rvh_init_synthetic_head)" if device_init else "host (scenes.synthetic_head) + upload",
+                   "scene_init": "reference scene frozen from Hair::Hair (tests/golden/c1_reference_scene.npz) + upload" if c1 else ("GPU (rvh_init_synthetic_head)" if device_init else "host (scenes.synthetic_head) + upload"),
                    "dt": DT, "l2": "state %.0f MB per GPU > 126 MB L2, no flush needed" % (S * N * 24 / 1e6) if S * N * 24 > 126e6 else "state %.1f MB is L2-resident (launch/latency-bound config)" % (S * N * 24 / 1e6),
                    "parallelism": "strand-sharded x%d, grid exchange per step: %s" % (world, exchange) if world > 1 else "1 GPU",
                    "strands_per_thread": int(sim.cfg.strands_per_thread),

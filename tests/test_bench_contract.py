@@ -1,0 +1,45 @@
+"""bench.py contract checks that need no GPU: the reference arm prints ONE JSON line with the agreed keys, and the
+workload table covers BASELINE.json's configs."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_prints_the_contract_line_for_the_shipped_scene():
+    d = _run("--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "1")
+    assert d["impl"] == "reference" and d["metric"] == "strand-point updates/sec" and d["unit"] == "strand-point updates/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"] == "c1" and d["config"]["points_per_strand"] == 10
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "c1"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_workload_table_names_every_baseline_config():
+    sys.path.insert(0, ROOT)
+    import bench
+    for w in ("c1", "c2", "c3", "c4", "c5", "ns_full", "ns_nogrid", "c3_sdf"):
+        S, N, L, flags, desc = bench.WORKLOADS[w]
+        assert S >= 900 and N >= 10 and desc
+    assert bench.WORKLOADS["c1"][:2] == (900, 10) and bench.WORKLOADS["c5"][:2] == (4000000, 32)
+    b1, b2 = bench.bytes_per_strand(32, True)
+    assert b1 == 48 * 31 + 12 and b2 == 36 * 31                     # B1 and B2 - B1
