@@ -375,3 +375,26 @@ def test_full_size_properties_1m_x_32():
     sim.close()
     ref, _ = orc.step(p, cols, DT, 0.25, st[sub])
     check_state(out[sub], ref, float(rest), N, what="1Mx32 subset")
+
+
+def test_interop_import_rejects_a_bad_handle_without_side_effects():
+    """rvh_import_strands_fd needs a VK_KHR_external_memory_fd handle; there is no Vulkan device in this image, so only the
+    failure path can be exercised: a bogus fd must come back as an error code + message, and the context must keep working."""
+    import ctypes as C
+    S, N = 256, 8
+    cols = rvh.scenes.reference_colliders()
+    st = synth(S, N, 2.5)
+    cfg = rvh.default_config(S, N, flags=rvh.GRID_ON)
+    sim = rvh.HairSim(cfg)
+    sim.set_colliders(cols)
+    sim.upload(st)
+    r = sim.L.rvh_import_strands_fd(sim.ctx, -1, sim.aos_bytes)
+    assert r < 0 and sim.L.rvh_last_error(sim.ctx)
+    r = sim.L.rvh_import_strands_fd(sim.ctx, 0, sim.aos_bytes - 16)        # smaller than Strand[S]
+    assert r == -1
+    sim.step(DT, 0.0)
+    out = sim.download()
+    sim.close()
+    rest = np.float32(2.5) / np.float32(N - 1)
+    ref, _ = orc.step(orc.default_params(S, N, orc.GRID_ON, rest_length=rest), cols, DT, 0.0, st)
+    check_state(out, ref, float(rest), N, what="after failed import")
