@@ -113,10 +113,13 @@ int fail(rvh_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
     return code;
 }
+// A failed runtime call also latches its code as the thread's "last error"; it is cleared here so that a recoverable failure
+// (e.g. an import with a bad handle) is not reported again by the cudaGetLastError() check after the next kernel launch.
 #define CU(call)                                                                            \
     do { cudaError_t e_ = (call);                                                           \
-         if (e_ != cudaSuccess)                                                             \
-             return fail(ctx, RVH_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+         if (e_ != cudaSuccess) {                                                           \
+             cudaGetLastError();                                                            \
+             return fail(ctx, RVH_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } \
     } while (0)
 
 void prof_begin(rvh_ctx* c, int kind) {
