@@ -81,6 +81,10 @@ struct rvh_ctx {
     int sdf_mode = 0;                     // 0 = no volume, 1 = plain loads, 2 = TMA-staged tiles
     CUtensorMap sdf_map;                  // 3-D tiled map of the volume, box 8x4x4 nodes (zeroed when unused)
     float* bake_tris = nullptr;
+    // collider candidate mask (StepParams::cmask)
+    unsigned char* cmask_dev = nullptr;
+    std::vector<unsigned char> cmask_host;
+    std::vector<float> cmask_ell;         // the ellipsoid floats the mask was built from
     // guide -> render strand expansion (k_expand_strands)
     ExpandTables* exp_tab = nullptr; int exp_I = 0, exp_D = 0;
     float4* exp_pw = nullptr; float4* exp_tu = nullptr; size_t exp_cap = 0;   // vertices allocated
@@ -146,13 +150,47 @@ void prof_collect(rvh_ctx* c) {   // caller has synchronised the stream
     c->pev_used = 0;
 }
 
+// Collider candidate mask (rvh_kernels.cuh gather_pack): one byte per coarse box of 2x2x2 grid cells, bit j set when ellipsoid
+// j (collider j+1) can contain a point of the box.  With q(p) = A p + t the ellipsoid's unit-space map, every p of a box with
+// centre c and half-diagonal r has |q(p)| >= |q(c)| - ||A||_F r, so the bit is cleared only where that bound exceeds 1 (plus a
+// margin for the rounding of the cell index).  Rebuilt only when an ellipsoid changes; the sphere moves every frame
+// (Scene.cpp:110-136) and is tested analytically, outside the mask.
+int update_collider_mask(rvh_ctx* ctx, const float* colliders, int n) {
+    StepParams& P = ctx->P;
+    const int G = P.G, D = G / 2, ne = n > 0 ? n - 1 : 0;
+    const bool usable = (ctx->cfg.flags & RVH_GRID_ON) && !(ctx->cfg.flags & RVH_SDF_ON) && (G % 2 == 0) && ne > 0 && ne <= 8 && !std::getenv("RVH_NO_CMASK");
+    if (!usable) { P.cmask = nullptr; P.cmask_dim = 0; return RVH_OK; }
+    const std::vector<float> ell(colliders + 48, colliders + 48 * (size_t)n);
+    if (ctx->cmask_dev && ell == ctx->cmask_ell) return RVH_OK;
+    ctx->cmask_host.assign((size_t)D * D * D, 0);
+    const float h2 = 2.0f * P.h, r = 1.7320508f * P.h * 1.01f + 1e-4f;
+    for (int j = 0; j < ne; ++j) {
+        const float* I = colliders + 48 * (size_t)(j + 1) + 16;           // Collider::inv, column-major
+        double fro = 0.0;
+        for (int c = 0; c < 3; ++c) for (int rr = 0; rr < 3; ++rr) fro += (double)I[c * 4 + rr] * I[c * 4 + rr];
+        const float bound = 1.0f + (float)std::sqrt(fro) * r + 1e-3f;
+        for (int z = 0; z < D; ++z) for (int y = 0; y < D; ++y) for (int x = 0; x < D; ++x) {
+            const float cx = P.origin[0] + h2 * ((float)x + 0.5f), cy = P.origin[1] + h2 * ((float)y + 0.5f), cz = P.origin[2] + h2 * ((float)z + 0.5f);
+            const float qx = I[0] * cx + I[4] * cy + I[8] * cz + I[12], qy = I[1] * cx + I[5] * cy + I[9] * cz + I[13], qz = I[2] * cx + I[6] * cy + I[10] * cz + I[14];
+            if (std::sqrt(qx * qx + qy * qy + qz * qz) <= bound) ctx->cmask_host[(size_t)x + (size_t)D * (y + (size_t)D * z)] |= (unsigned char)(1u << j);
+        }
+    }
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->cmask_dev) CU(cudaMalloc(&ctx->cmask_dev, ctx->cmask_host.size()));
+    CU(cudaMemcpyAsync(ctx->cmask_dev, ctx->cmask_host.data(), ctx->cmask_host.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cmask_ell = ell;
+    P.cmask = ctx->cmask_dev; P.cmask_dim = D;
+    return RVH_OK;
+}
+
 template <int V, bool WIND, int NELL>
 void launch_k1(rvh_ctx* c, int gather) {
     // gather: 0 = none pending, 1 = friction, 2 = friction + repulsion (extension: V <= 2 only, see create_impl)
     if (gather == 2) {
         if constexpr (V <= 2) k_ftl_step<V, WIND, NELL, 2><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map);
     } else if (gather == 1) k_ftl_step<V, WIND, NELL, 1><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map);
-    else                    k_ftl_step<V, WIND, NELL, 0><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map);
+    else if constexpr (NELL < 100) k_ftl_step<V, WIND, NELL, 0><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map);
 }
 template <int V>
 void launch_k1_v(rvh_ctx* c, bool wind, int gather) {
@@ -164,6 +202,12 @@ void launch_k1_v(rvh_ctx* c, bool wind, int gather) {
         return;
     }
     const bool five = c->P.n_ell == 5;     // the reference scene's collider count gets the unrolled kernel
+    // collider candidate mask: pays when the kernel is throughput-bound (several waves of CTAs); with few CTAs the kernel is
+    // latency-bound and the mask lookup in front of the ellipsoid tests only lengthens the chain (C3: 0.133 -> 0.149 ms)
+    if (five && gather && c->P.cmask && c->k1_blocks >= 4 * 148) {
+        if (wind) launch_k1<V, true, 105>(c, gather); else launch_k1<V, false, 105>(c, gather);
+        return;
+    }
     if (wind) { if (five) launch_k1<V, true, 5>(c, gather); else launch_k1<V, true, -1>(c, gather); }
     else      { if (five) launch_k1<V, false, 5>(c, gather); else launch_k1<V, false, -1>(c, gather); }
 }
@@ -471,7 +515,7 @@ int rvh_set_colliders(rvh_ctx* ctx, const void* colliders, int n) {
             for (int k = 0; k < 3; ++k) E.nt[r * 3 + k] = IT[k * 4 + r];
     }
     ctx->colliders_set = true;
-    return RVH_OK;
+    return update_collider_mask(ctx, c, n);
 }
 
 static int unpack_from_staging(rvh_ctx* ctx) {
@@ -901,6 +945,7 @@ void rvh_destroy(rvh_ctx* c) {
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->interop_aos) cudaFree(c->interop_aos);
     if (c->interop_mem) cudaDestroyExternalMemory(c->interop_mem);
+    cudaFree(c->cmask_dev);
     cudaFree(c->sdf_dev); cudaFree(c->bake_tris); cudaFree(c->exp_tab); cudaFree(c->exp_pw); cudaFree(c->exp_tu);
     cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->fgrid); cudaFree(c->perm); cudaFree(c->aos_dev);
     cudaFree(c->sort_tmp); cudaFree(c->sort_keys); cudaFree(c->sort_keys_out); cudaFree(c->sort_ids);

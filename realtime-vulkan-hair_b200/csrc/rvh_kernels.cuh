@@ -64,6 +64,8 @@ struct StepParams {
     int wind_mode;                          // 0 off, 1 = variant A (:151), 2 = variant B (:152)
     float wind_s2T, wind_T3, wind_amp;      // 2*sin(2T); 3T mod 2pi; 10 (A) or 7*fbm(sinT,cosT) (B)
     int int32_wrap, keep_corr;
+    const unsigned char* cmask;             // collider candidate mask over the grid box at half resolution (see gather_pack); null = none
+    int cmask_dim;                          // G / 2
     SdfVolume sdf;                          // RVH_SDF_ON
     float repulsion, inv_h;                 // RVH_REPULSION_ON: v -= repulsion * h*grad(rho)/sum(D) (gather_pack); inv_h = 1/h
 };
@@ -215,8 +217,12 @@ __device__ __forceinline__ void splat_point_direct(const StepParams& P, unsigned
 // cell f+1, times 1/h), the velocity also gets  v -= repulsion * h * grad(rho) / sum_c D_c  after the friction blend: a push
 // down the density gradient whose every component is bounded by `repulsion` whatever the strand count (|h grad rho| <= sum D).
 // Oracle twin: oracle.c gather_strand.
-template <class T, bool REP>
-__device__ __forceinline__ void gather_pack(const StepParams& P, const float4* __restrict__ fgrid, T px, T py, T pz, T& vx, T& vy, T& vz) {
+// Collider candidates: the gather has each point's grid cell in hand anyway, so it also looks up a host-built byte per
+// coarse (2x2x2-cell) box: bit j set <=> ellipsoid j can contain a point of that box (conservative).  `cand` returns the OR
+// over the pack (all ones when a point is outside the grid); the caller ORs it over the warp and k_ftl_step then runs only
+// the ellipsoid tests that can hit -- typically 1-2 of 5, each worth 12 FFMA2 and as many constant loads.
+template <class T, bool REP, bool CMASK = false>
+__device__ __forceinline__ void gather_pack(const StepParams& P, const float4* __restrict__ fgrid, T px, T py, T pz, T& vx, T& vy, T& vz, unsigned& cand) {
     constexpr int n = VecTraits<T>::n;
     float rho[n], rgx[n], rgy[n], rgz[n];
 #pragma unroll
@@ -231,6 +237,13 @@ __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* _
         interior = interior && cell_ok(X.f[i], P.G - 1) && cell_ok(Y.f[i], P.G - 1) && cell_ok(Z.f[i], P.G - 1) && !isnan_[i];
     }
     const T xy[4] = { vmul(X.w0, Y.w0), vmul(X.w1, Y.w0), vmul(X.w0, Y.w1), vmul(X.w1, Y.w1) };
+    cand = ~0u;
+    if (CMASK && interior) {
+        cand = 0u;
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+            cand |= __ldg(P.cmask + ((X.f[i] >> 1) + ((Y.f[i] >> 1) + (Z.f[i] >> 1) * P.cmask_dim) * P.cmask_dim));
+    }
     if (interior) {                                                     // all 8 corners of every point are cells
         const float4* base[n];
 #pragma unroll
@@ -474,16 +487,23 @@ __device__ __forceinline__ void collision_force(const StepParams& P, const SdfTi
     ox = ax * ih; oy = ay * ih; oz = az * ih;
 }
 
-// NELL >= 0: number of ellipsoids known at compile time; NELL == -1: run-time count; NELL <= -2: the head SDF replaces
-// the ellipsoids (-2 plain loads, -3 TMA-staged tile in `tile`).
+// NELL >= 0: number of ellipsoids known at compile time (+100: with the collider candidate mask); NELL == -1: run-time
+// count; NELL <= -2: the head SDF replaces the ellipsoids (-2 plain loads, -3 TMA-staged tile in `tile`).
 // GATHER != 0: the previous step's gather (+ repulsion when 2) is applied to (vx,vy,vz) right before they are first used,
 // i.e. AFTER the collision tests, whose work hides the latency of the cells prefetched at the top.
 template <class T, bool WIND, int NELL, int GATHER>
 __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const SdfTile& tile, const float4* __restrict__ fgrid,
                                                     T cx, T cy, T cz, T vx, T vy, T vz, T parx, T pary, T parz) {
     constexpr int n = VecTraits<T>::n;
+    // NELL >= 100: NELL - 100 unrolled ellipsoids, tested only where the collider candidate mask allows (needs GATHER)
+    constexpr bool CMASK = NELL >= 100 && GATHER != 0 && !RVH_K1_PREFETCH;
+    constexpr int NE = NELL >= 100 ? NELL - 100 : NELL;
+    unsigned cand = ~0u;                                                // ellipsoids that can hit a point of this warp's row
     if (GATHER && RVH_K1_PREFETCH) gather_prefetch<T>(P, fgrid, cx, cy, cz);
-    if (GATHER && !RVH_K1_PREFETCH) gather_pack<T, GATHER == 2>(P, fgrid, cx, cy, cz, vx, vy, vz);
+    if (GATHER && !RVH_K1_PREFETCH) {
+        gather_pack<T, GATHER == 2, CMASK>(P, fgrid, cx, cy, cz, vx, vy, vz, cand);
+        if (CMASK) cand = __reduce_or_sync(0xffffffffu, cand);          // warp-uniform: the skipped tests cost no divergence
+    }
     T fx = bc<T>(0.0f), fy = bc<T>(P.gravity_y), fz = bc<T>(0.0f);       // :150
     if (WIND) {
         const T a1 = vmul(cy, bc<T>(10.0f));
@@ -515,15 +535,16 @@ __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const S
 #pragma unroll
         for (int i = 0; i < n; ++i) hit[i] = (el(d2, i) < P.sphere_r2) ? (unsigned)P.has_sphere : 0u;   // :162
     }
-    if (NELL >= 0) {
+    if (NE >= 0) {
 #pragma unroll
-        for (int j = 0; j < (NELL >= 0 ? NELL : 0); ++j) {
+        for (int j = 0; j < (NE >= 0 ? NE : 0); ++j) {
+            if (CMASK && !(cand & (1u << j))) continue;
             T qx, qy, qz;
             const T q2 = ellipsoid_q<T>(P.ell[j], cx, cy, cz, qx, qy, qz);
 #pragma unroll
             for (int i = 0; i < n; ++i) if (el(q2, i) <= 1.0f) hit[i] |= 2u << j;                       // :66
         }
-    } else if (NELL == -1) {
+    } else if (NE == -1) {
         for (int j = 0; j < P.n_ell; ++j) {
             T qx, qy, qz;
             const T q2 = ellipsoid_q<T>(P.ell[j], cx, cy, cz, qx, qy, qz);
@@ -550,7 +571,7 @@ __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const S
         fx = vadd(fx, ax); fy = vadd(fy, ay); fz = vadd(fz, az);
     }
 
-    if (GATHER && RVH_K1_PREFETCH) gather_pack<T, GATHER == 2>(P, fgrid, cx, cy, cz, vx, vy, vz);
+    if (GATHER && RVH_K1_PREFETCH) { unsigned late; gather_pack<T, GATHER == 2>(P, fgrid, cx, cy, cz, vx, vy, vz, late); }
     PointOut<T> o;
     const T dt = bc<T>(P.dt), dt2 = bc<T>(P.dt2);
     const T prx = vfma(dt2, fx, vfma(dt, vx, cx));                      // :187
@@ -616,7 +637,7 @@ template <int V> __device__ __forceinline__ void store_packs(float* __restrict__
 #define RVH_K1_MINBLOCKS 6      // <= 85 registers: 6 CTAs/SM measured fastest on B200 (5: 0.365 ms, 6: 0.357 ms, 7: 0.416 ms at 1M x 32)
 #endif
 #ifndef RVH_K1G_MINBLOCKS
-#define RVH_K1G_MINBLOCKS 6     // with the fused gather (1M x 32, all on): 4 CTAs/SM 0.383 ms, 5: 0.363 ms, 6 (<= 85 registers, a few spills): 0.356 ms
+#define RVH_K1G_MINBLOCKS 5     // with the fused gather (1M x 32, all on, collider candidate mask): 5 CTAs/SM (96 registers) 0.343 ms, 6 (80 registers, spills in the row loop) 0.406 ms; without the mask 4: 0.383, 5: 0.363, 6: 0.356 ms
 #endif
 #ifndef RVH_K1_UNROLL
 #define RVH_K1_UNROLL 1
@@ -1085,7 +1106,8 @@ k_grid_gather(const __grid_constant__ StepParams P, float* __restrict__ planes, 
         float* q = planes + tiled_index(6, P.S_pad, (int)row + 1, 0, (int)s0);   // skip the root row
         const float2 px = *reinterpret_cast<const float2*>(q), py = *reinterpret_cast<const float2*>(q + plane), pz = *reinterpret_cast<const float2*>(q + 2 * plane);
         float2 vx = *reinterpret_cast<const float2*>(q + 3 * plane), vy = *reinterpret_cast<const float2*>(q + 4 * plane), vz = *reinterpret_cast<const float2*>(q + 5 * plane);
-        gather_pack<float2, REP>(P, fgrid, px, py, pz, vx, vy, vz);
+        unsigned cand;
+        gather_pack<float2, REP>(P, fgrid, px, py, pz, vx, vy, vz, cand);
         *reinterpret_cast<float2*>(q + 3 * plane) = vx; *reinterpret_cast<float2*>(q + 4 * plane) = vy; *reinterpret_cast<float2*>(q + 5 * plane) = vz;
     }
 }

@@ -398,3 +398,32 @@ def test_interop_import_rejects_a_bad_handle_without_side_effects():
     rest = np.float32(2.5) / np.float32(N - 1)
     ref, _ = orc.step(orc.default_params(S, N, orc.GRID_ON, rest_length=rest), cols, DT, 0.0, st)
     check_state(out, ref, float(rest), N, what="after failed import")
+
+
+@pytest.mark.parametrize("S,N,spt", [(160000, 16, 2), (80000, 24, 1)])         # >= 4 x 148 CTAs of 128 threads: the masked kernel is used
+def test_collider_candidate_mask_never_drops_a_collision(S, N, spt):
+    """In steady-state stepping k_ftl_step runs only the ellipsoid tests its collider candidate mask allows (gather_pack).
+    Stepping with a read-back in between forces the unmasked kernel (no gather pending), so the two must agree, on a scene
+    whose hair lies on the head, neck and shoulders."""
+    L = 2.5
+    cols = rvh.scenes.bench_colliders()
+    rest = np.float32(L) / np.float32(N - 1)
+    p = orc.default_params(S, N, orc.GRID_ON, rest_length=rest)
+    st = synth(S, N, L, seed_vel=21)
+    for k in range(50):                                   # oracle free run: drape the hair over head, bust and shoulders
+        st, _ = orc.step(p, cols, DT, 0.0, st, threads=8)
+    inv = cols[1:, 16:32].reshape(-1, 4, 4).transpose(0, 2, 1)                 # Collider::inv, row-major
+    pts = np.concatenate([st[:, 0, 1:, :3].reshape(-1, 3), np.ones((S * (N - 1), 1), np.float32)], axis=1)
+    inside = (np.linalg.norm(np.einsum("jrc,pc->jpr", inv, pts)[..., :3], axis=-1) <= 1.0)
+    assert inside.any(axis=0).mean() > 0.05 and (inside.sum(axis=1) > 0).sum() >= 3, "scene must engage several ellipsoids"
+    cfg = rvh.default_config(S, N, flags=rvh.GRID_ON, rest_length=float(rest), strands_per_thread=spt)
+    a = rvh.HairSim(cfg); a.set_colliders(cols); a.upload(st)
+    b = rvh.HairSim(cfg); b.set_colliders(cols); b.upload(st)
+    for k in range(4):
+        a.step(DT, 0.0)                                    # fused gather + masked collider tests from step 2 on
+        b.step(DT, 0.0)
+        b.upload(b.download())                             # stand-alone gather, next step tests every ellipsoid
+    fa, fb = a.download(), b.download()
+    a.close(); b.close()
+    assert np.abs(fa[:, 0, :, :3] - fb[:, 0, :, :3]).max() <= 2e-5
+    assert np.abs(fa[:, 1, :, :3] - fb[:, 1, :, :3]).max() <= 2e-3
