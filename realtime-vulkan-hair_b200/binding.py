@@ -238,6 +238,7 @@ class HairSim:
         return list(out)
 
     def profile_enable(self, on=True):
+        """False/0 off, True/1 every kernel, 2 only k_ftl_step."""
         self._check(self.L.rvh_profile_enable(self.ctx, int(on)), "rvh_profile_enable")
 
     def profile_read(self):

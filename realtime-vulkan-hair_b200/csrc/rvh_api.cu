@@ -102,7 +102,8 @@ struct rvh_ctx {
     // timing
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     float last_ms = 0.f;
-    bool profiling = false;
+    int profiling = 0;                    // 0 off, 1 every kernel, 2 only k_ftl_step (the roofline kernel: 2 events per step instead of 10)
+    bool prof_open = false;
     std::vector<cudaEvent_t> pev;         // pairs, recycled
     std::vector<int> pev_kind; size_t pev_used = 0;
     float prof_ms[EV_COUNT] = { 0, 0, 0, 0, 0, 0 };
@@ -127,7 +128,8 @@ int fail(rvh_ctx* c, int code, const std::string& msg) {
     } while (0)
 
 void prof_begin(rvh_ctx* c, int kind) {
-    if (!c->profiling) return;
+    c->prof_open = c->profiling == 1 || (c->profiling == 2 && kind == EV_K1);
+    if (!c->prof_open) return;
     if (c->pev_used + 2 > c->pev.size()) {
         cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
         c->pev.push_back(a); c->pev.push_back(b); c->pev_kind.push_back(kind);
@@ -136,7 +138,8 @@ void prof_begin(rvh_ctx* c, int kind) {
     cudaEventRecord(c->pev[c->pev_used], c->stream);
 }
 void prof_end(rvh_ctx* c) {
-    if (!c->profiling) return;
+    if (!c->prof_open) return;
+    c->prof_open = false;
     cudaEventRecord(c->pev[c->pev_used + 1], c->stream);
     c->pev_used += 2;
 }
@@ -908,7 +911,7 @@ int rvh_draw_indirect(rvh_ctx* ctx, uint32_t out[4]) {
 
 int rvh_profile_enable(rvh_ctx* ctx, int on) {
     if (!ctx) return RVH_ERR_INVALID;
-    ctx->profiling = on != 0;
+    ctx->profiling = on < 0 ? 0 : (on > 2 ? 1 : on);
     return RVH_OK;
 }
 
