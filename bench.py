@@ -82,8 +82,10 @@ def bytes_per_strand(N, grid):
 
 
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region: NVML polled every ~2 ms from a thread (the timed region is
-    tens of milliseconds, too short for `nvidia-smi -lms`); falls back to one nvidia-smi query."""
+    """SM clock + throttle reasons DURING the timed region: NVML polled from a thread (`nvidia-smi -lms 200`, the recipe's
+    line, is too coarse for a timed region of a quarter of a second); falls back to one nvidia-smi query.  The period
+    matters: NVML queries are not free for the GPU -- polling every 2 ms slowed the step by 3.6 % (splat 0.425 -> 0.467 ms),
+    so the poll runs every 25 ms and the cost that remains is reported (`roofline.sampler_overhead_ms_per_step`)."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -91,6 +93,7 @@ class ClockSampler:
         self.stop_flag = threading.Event()
         self.thread = None
         self.max_mhz = None
+        self.period = 0.025
 
     def _poll(self):
         import pynvml as nv
@@ -107,7 +110,7 @@ class ClockSampler:
                 self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         try:
@@ -134,7 +137,7 @@ class ClockSampler:
         self.thread.join(timeout=2)
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
                 "samples": len(self.samples), "reasons": sorted(self.reasons),
-                "power_w_max": max(self.power) if self.power else None, "how": "NVML polled every 2 ms during the timed region"}
+                "power_w_max": max(self.power) if self.power else None, "how": "NVML polled every %d ms during the timed region" % int(self.period * 1e3)}
 
 
 # ---- the reference on the host cores ----------------------------------------------------------------------
@@ -261,7 +264,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="ns_full", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -352,8 +355,8 @@ def main():
 
     # ---- device-resident timed region -------------------------------------------------------
     sim.step_n(max(args.warmup, 3), DT, 0.0, timed=True)
-    # CUDA events around k_ftl_step ride inside the timed region (the roofline's launch duration comes from them); their
-    # cost is measured right after it (`event_overhead_ms_per_step`)
+    # CUDA events around k_ftl_step ride inside the timed region (the roofline's launch duration comes from them); what the
+    # timed region loses to them and to the clock sampler is measured right after it (`sampler_overhead_ms_per_step`)
     sim.profile_enable(0 if args.no_kernel_events else 2)       # timed region: events around the roofline kernel only
     sim.profile_read()
     launches0 = sim.kernel_launches()
@@ -368,9 +371,8 @@ def main():
     sim.profile_enable(False)
     launches = sim.kernel_launches() - launches0
     n2 = min(args.steps, 50)
-    ms_plain = sim.step_n(n2, DT, DT * (args.warmup + args.steps), timed=True) / n2      # same steps, no per-kernel events
-    # the split over ALL kernels comes from a separate, untimed pass: an event pair between two kernels costs ~3 us of stream
-    # time, 10 of them per step would take 3-4 % off the headline number
+    ms_plain = sim.step_n(n2, DT, DT * (args.warmup + args.steps), timed=True) / n2      # same steps with neither the clock sampler nor kernel events running
+    # the split over ALL kernels comes from a separate, untimed pass right after the timed region
     k1_timed = prof["ftl_step"]
     if not args.no_kernel_events:
         sim.profile_enable(1)
@@ -399,7 +401,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": S * b1, "avg_launch_ms": k1_ms, "per_kernel_ms": per_kernel,
                 "per_kernel_ms_source": "ftl_step: CUDA events inside the timed region; the other kernels: events in a separate pass of %d steps right after it" % n2,
-                "longest_kernel": dominant, "event_overhead_ms_per_step": max(0.0, ms / args.steps - ms_plain),
+                "longest_kernel": dominant, "sampler_overhead_ms_per_step": max(0.0, ms / args.steps - ms_plain),
                 "step_bytes": S * (b1 + b2), "step_frac": (S * (b1 + b2) / (ms / args.steps * 1e-3) / 1e9) / peak,
                 "note": "achieved = S*(48*(N-1)+12) bytes / CUDA-event time of k_ftl_step inside the timed region; step_frac = reference-shaped "
                         "step bytes S*(84*(N-1)+12) / whole step time"}
