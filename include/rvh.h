@@ -148,6 +148,10 @@ int rvh_bake_head_sdf_from_colliders(rvh_ctx* ctx, const int dim[3], const float
 int rvh_bake_head_sdf_from_mesh(rvh_ctx* ctx, const float* verts, int nverts, const int* tris, int ntris,
                                 const int dim[3], const float origin[3], float cell);
 int rvh_download_head_sdf(rvh_ctx* ctx, float* sdf, size_t bytes);     /* nx*ny*nz floats */
+/* Test hook: the collider candidate mask k_ftl_step consults in steady-state stepping: one byte per box
+ * of 2x2x2 grid cells, x fastest, bit j set when ellipsoid j (collider j+1) can contain a point of the box.  *dim receives
+ * grid_dim/2, or 0 when no mask is in use (then nothing is written). */
+int rvh_download_collider_mask(rvh_ctx* ctx, unsigned char* out, size_t bytes, int* dim);
 int rvh_sdf_mode(rvh_ctx* ctx);   /* 0 = no volume, 1 = plain loads (default), 2 = TMA-staged tiles (RVH_SDF_TMA) */
 
 /* ---- guide strands -> render strands -------------------------------------------------

@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "rvh_profile_enable", "rvh_profile_read", "rvh_sync", "rvh_last_step_ms", "rvh_kernel_launches",
     "rvh_last_error", "rvh_destroy", "rvh_collider_build", "rvh_collider_translate", "rvh_wind_fbm",
     "rvh_abi_version", "rvh_set_head_sdf", "rvh_bake_head_sdf_from_colliders", "rvh_bake_head_sdf_from_mesh",
-    "rvh_download_head_sdf", "rvh_sdf_mode", "rvh_expand_strands", "rvh_expand_device_buffers", "rvh_init_from_mesh",
+    "rvh_download_head_sdf", "rvh_sdf_mode", "rvh_expand_strands", "rvh_expand_device_buffers", "rvh_init_from_mesh", "rvh_download_collider_mask",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library():
     L.rvh_bake_head_sdf_from_mesh.argtypes = [vp, fp, C.c_int, ip, C.c_int, ip, fp, C.c_float]
     L.rvh_download_head_sdf.argtypes = [vp, fp, C.c_size_t]
     L.rvh_sdf_mode.argtypes = [vp]
+    L.rvh_download_collider_mask.argtypes = [vp, C.POINTER(C.c_ubyte), C.c_size_t, ip]
     L.rvh_expand_strands.argtypes = [vp, C.c_int, C.c_int, fp, fp, C.c_size_t, fp]
     L.rvh_init_from_mesh.argtypes = [vp, fp, fp, C.c_int, C.c_ulonglong, C.c_float, C.c_ulonglong]
     L.rvh_expand_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -280,6 +281,14 @@ class HairSim:
         out = np.empty((nz, ny, nx), np.float32)
         self._check(self.L.rvh_download_head_sdf(self.ctx, _fptr(out), out.nbytes), "rvh_download_head_sdf")
         return out
+
+    def collider_mask(self):
+        """uint8 [D, D, D] (z, y, x) candidate mask, or None when no mask is in use."""
+        D = self.cfg.grid_dim // 2
+        out = np.zeros((D, D, D), np.uint8)
+        dim = C.c_int(0)
+        self._check(self.L.rvh_download_collider_mask(self.ctx, out.ctypes.data_as(C.POINTER(C.c_ubyte)), out.nbytes, C.byref(dim)), "rvh_download_collider_mask")
+        return out if dim.value else None
 
     def sdf_mode(self):
         return {0: "off", 1: "ldg", 2: "tma"}[int(self.L.rvh_sdf_mode(self.ctx))]

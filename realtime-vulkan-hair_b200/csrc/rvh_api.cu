@@ -600,10 +600,11 @@ int rvh_init_from_mesh(rvh_ctx* ctx, const float* tri_pos, const float* tri_nrm,
     for (int t = 0; t < ntris; ++t) cdf[t] = (float)(acc[t] / total);
     cdf[ntris - 1] = 1.0f;
     CU(cudaSetDevice(ctx->cfg.device));
-    float *dpos = nullptr, *dnrm = nullptr, *dcdf = nullptr;
-    CU(cudaMalloc(&dpos, sizeof(float) * 9 * ntris));
-    CU(cudaMalloc(&dcdf, sizeof(float) * ntris));
-    if (tri_nrm) CU(cudaMalloc(&dnrm, sizeof(float) * 9 * ntris));
+    struct DevBuf { float* p = nullptr; ~DevBuf() { cudaFree(p); } } bpos, bnrm, bcdf;     // released on every return path
+    CU(cudaMalloc(&bpos.p, sizeof(float) * 9 * ntris));
+    CU(cudaMalloc(&bcdf.p, sizeof(float) * ntris));
+    if (tri_nrm) CU(cudaMalloc(&bnrm.p, sizeof(float) * 9 * ntris));
+    float *dpos = bpos.p, *dnrm = bnrm.p, *dcdf = bcdf.p;
     cudaError_t e = cudaMemcpyAsync(dpos, tri_pos, sizeof(float) * 9 * ntris, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dcdf, cdf.data(), sizeof(float) * ntris, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && tri_nrm) e = cudaMemcpyAsync(dnrm, tri_nrm, sizeof(float) * 9 * ntris, cudaMemcpyHostToDevice, ctx->stream);
@@ -615,7 +616,6 @@ int rvh_init_from_mesh(rvh_ctx* ctx, const float* tri_pos, const float* tri_nrm,
     }
     int r = e == cudaSuccess ? unpack_from_staging(ctx) : fail(ctx, RVH_ERR_CUDA, std::string("rvh_init_from_mesh: ") + cudaGetErrorString(e));
     cudaStreamSynchronize(ctx->stream);                      // the pageable host arrays and the temporaries are released now
-    cudaFree(dpos); cudaFree(dnrm); cudaFree(dcdf);
     return r;
 }
 
@@ -730,6 +730,18 @@ int rvh_download_head_sdf(rvh_ctx* ctx, float* sdf, size_t bytes) {
 }
 
 int rvh_sdf_mode(rvh_ctx* ctx) { return ctx ? ctx->sdf_mode : 0; }
+
+int rvh_download_collider_mask(rvh_ctx* ctx, unsigned char* out, size_t bytes, int* dim) {
+    if (!ctx) return RVH_ERR_INVALID;
+    const int D = ctx->P.cmask ? ctx->P.cmask_dim : 0;
+    if (dim) *dim = D;
+    if (!D) return RVH_OK;                                     // no mask in use (grid off, SDF on, odd grid_dim, no ellipsoids)
+    if (!out || bytes != (size_t)D * D * D) return fail(ctx, RVH_ERR_INVALID, "collider mask is (grid_dim/2)^3 bytes");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(out, ctx->cmask_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RVH_OK;
+}
 
 
 // ---- guide strand -> render strands (hair.tesc / hair.tese) -------------------------------------------------

@@ -427,3 +427,31 @@ def test_collider_candidate_mask_never_drops_a_collision(S, N, spt):
     a.close(); b.close()
     assert np.abs(fa[:, 0, :, :3] - fb[:, 0, :, :3]).max() <= 2e-5
     assert np.abs(fa[:, 1, :, :3] - fb[:, 1, :, :3]).max() <= 2e-3
+
+
+def test_collider_candidate_mask_is_conservative():
+    """Every point inside ellipsoid j (|inv_j (p,1)| <= 1, compute.comp:64-67) must lie in a box whose mask byte has bit j."""
+    rng = np.random.default_rng(11)
+    for cols in (rvh.scenes.bench_colliders(), rvh.scenes.reference_colliders()):
+        sim = rvh.HairSim(rvh.default_config(256, 4, flags=rvh.GRID_ON))
+        sim.set_colliders(cols)
+        mask = sim.collider_mask()
+        sim.close()
+        assert mask is not None and mask.shape == (32, 32, 32)
+        h2 = 2 * 7.0 / 64
+        origin = np.array([-3, -2, -5], np.float64)
+        for j in range(5):
+            X = cols[1 + j, 0:16].reshape(4, 4).T.astype(np.float64)                 # transform: unit sphere -> ellipsoid
+            u = rng.normal(size=(200000, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+            u *= rng.uniform(0, 1, (200000, 1)) ** (1 / 3)                            # uniform in the unit ball
+            p = u @ X[:3, :3].T + X[:3, 3]
+            b = np.floor((p - origin) / h2).astype(int)
+            ok = np.all((b >= 0) & (b < 32), axis=1)                                  # points outside the grid never consult the mask
+            bits = mask[b[ok, 2], b[ok, 1], b[ok, 0]]
+            assert np.all(bits & (1 << j)), "ellipsoid %d: %d interior points in unflagged boxes" % (j, int(np.sum((bits & (1 << j)) == 0)))
+        # and it prunes: most boxes allow at most two ellipsoids
+        assert (np.unpackbits(mask.reshape(-1, 1), axis=1).sum(axis=1) <= 2).mean() > 0.8
+    sim = rvh.HairSim(rvh.default_config(256, 4, flags=0))                            # grid off: no mask
+    sim.set_colliders(rvh.scenes.bench_colliders())
+    assert sim.collider_mask() is None
+    sim.close()
