@@ -95,22 +95,25 @@ class ClockSampler:
         self.max_mhz = None
         self.period = 0.025
 
-    def _poll(self):
+    def _sample(self):
         import pynvml as nv
         h = self.h
         names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
                  nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+        self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        for bit, nm in names.items():
+            if r & bit:
+                self.reasons.add(nm)
+        self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+
+    def _poll(self):
         while not self.stop_flag.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                self._sample()
             except Exception:
                 break
-            time.sleep(self.period)
+            self.stop_flag.wait(self.period)
 
     def start(self):
         try:
@@ -135,6 +138,10 @@ class ClockSampler:
                 return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock query unavailable"]}
         self.stop_flag.set()
         self.thread.join(timeout=2)
+        try:
+            self._sample()                      # one more right at the end of the timed region (short runs: K steps may last < one period)
+        except Exception:
+            pass
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
                 "samples": len(self.samples), "reasons": sorted(self.reasons),
                 "power_w_max": max(self.power) if self.power else None, "how": "NVML polled every %d ms during the timed region" % int(self.period * 1e3)}
