@@ -62,6 +62,7 @@ struct rvh_ctx {
     unsigned long long* grid = nullptr;   // [G^3][4] int64 accumulators
     float4* fgrid = nullptr;              // [G^3] float cells for the gather (k_grid_finalize)
     int k1_blocks = 0;
+    uint4* k1_clear = nullptr; unsigned k1_clear_n = 0;    // grid clear fused into k_ftl_step (set per step)
     size_t grid_bytes = 0;
     int* perm = nullptr;                  // internal -> external strand index (Morton order)
     void* aos_dev = nullptr;              // Strand[S] staging / interop target
@@ -191,9 +192,9 @@ template <int V, bool WIND, int NELL>
 void launch_k1(rvh_ctx* c, int gather) {
     // gather: 0 = none pending, 1 = friction, 2 = friction + repulsion (extension: V <= 2 only, see create_impl)
     if (gather == 2) {
-        if constexpr (V <= 2) k_ftl_step<V, WIND, NELL, 2><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map);
-    } else if (gather == 1) k_ftl_step<V, WIND, NELL, 1><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map);
-    else if constexpr (NELL < 100) k_ftl_step<V, WIND, NELL, 0><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map);
+        if constexpr (V <= 2) k_ftl_step<V, WIND, NELL, 2><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
+    } else if (gather == 1) k_ftl_step<V, WIND, NELL, 1><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
+    else if constexpr (NELL < 100) k_ftl_step<V, WIND, NELL, 0><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
 }
 template <int V>
 void launch_k1_v(rvh_ctx* c, bool wind, int gather) {
@@ -260,9 +261,14 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
     if ((flags & RVH_SDF_ON) && !ctx->sdf_dev)
         return fail(ctx, RVH_ERR_STATE, "RVH_SDF_ON but no head SDF: call rvh_set_head_sdf or rvh_bake_head_sdf_* first");
     if (phases & 1) {
-        if (grid) {
+        // Renderer.cpp:2063.  Wide launches clear the grid from inside k_ftl_step (<= 4 stores of 16 bytes per thread)
+        const size_t clear_n = ctx->grid_bytes / 16;
+        const bool fused_clear = grid && (size_t)ctx->k1_blocks * kBlock * 4 >= clear_n && clear_n < ((size_t)1 << 32) && !std::getenv("RVH_NO_FUSED_CLEAR");
+        ctx->k1_clear = fused_clear ? reinterpret_cast<uint4*>(ctx->grid) : nullptr;
+        ctx->k1_clear_n = fused_clear ? (unsigned)clear_n : 0u;
+        if (grid && !fused_clear) {
             prof_begin(ctx, EV_CLEAR);
-            CU(cudaMemsetAsync(ctx->grid, 0, ctx->grid_bytes, ctx->stream));   // Renderer.cpp:2063
+            CU(cudaMemsetAsync(ctx->grid, 0, ctx->grid_bytes, ctx->stream));
             prof_end(ctx);
         }
         prof_begin(ctx, EV_K1);

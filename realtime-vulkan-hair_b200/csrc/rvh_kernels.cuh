@@ -680,10 +680,15 @@ __device__ __forceinline__ void sdf_stage_row(const StepParams& P, const CUtenso
 template <int V, bool WIND, int NELL, int GATHER>
 __global__ void __launch_bounds__(kBlock, (NELL <= -2 || GATHER == 2) ? RVH_K1X_MINBLOCKS : (GATHER ? RVH_K1G_MINBLOCKS : RVH_K1_MINBLOCKS))
 k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr,
-           const float4* __restrict__ fgrid, const __grid_constant__ CUtensorMap sdf_map) {
+           const float4* __restrict__ fgrid, const __grid_constant__ CUtensorMap sdf_map, uint4* __restrict__ grid_clear, unsigned grid_clear_n) {
     using T = typename PackOf<V>::T;
     constexpr int NP = PackOf<V>::n;
     constexpr bool TMA = NELL == -3;
+    // The step's grid clear (Renderer.cpp:2063) rides here when the launch is wide enough: this kernel never touches the
+    // int64 accumulators (it reads the float grid), the splat that fills them comes after it in the stream, and whoever
+    // read them last (finalize / exchange / a download) came before it.  Saves the memset launch.
+    if (grid_clear)
+        for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < grid_clear_n; k += gridDim.x * blockDim.x) grid_clear[k] = make_uint4(0u, 0u, 0u, 0u);
     __shared__ __align__(128) unsigned char sdf_raw[TMA ? sizeof(SdfStageSmem) : 16];
     SdfStageSmem& sm = *reinterpret_cast<SdfStageSmem*>(sdf_raw);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
