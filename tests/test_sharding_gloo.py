@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, S, N, L, out_path):
+def _worker(rank, world, port, S, N, L, extra, out_path):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -35,7 +35,7 @@ def _worker(rank, world, port, S, N, L, out_path):
     lo, hi = rvh.scenes.shard_range(S, rank, world)
     st = rvh.scenes.synthetic_head(hi - lo, N, L, first_strand=lo, colliders=cols)     # every rank makes exactly its shard
     rest = np.float32(L) / np.float32(N - 1)
-    p = orc.default_params(hi - lo, N, orc.GRID_ON | orc.WIND_B, rest_length=rest)
+    p = orc.default_params(hi - lo, N, orc.GRID_ON | orc.WIND_B | extra, rest_length=rest)
     for k in range(2):
         T = np.float32(0.25) + np.float32(k) * dt
         st = orc.phase_integrate(p, cols, dt, T, st)
@@ -52,19 +52,19 @@ def _worker(rank, world, port, S, N, L, out_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("S,N,L", [(3001, 16, 0.4), (2048, 32, 2.5)])
-def test_two_rank_sharded_step_equals_single_process(tmp_path, S, N, L):
+@pytest.mark.parametrize("S,N,L,extra", [(3001, 16, 0.4, 0), (2048, 32, 2.5, 0), (2500, 12, 0.4, 128)])     # 128 = ORC_REPULSION_ON: reads the reduced grid too
+def test_two_rank_sharded_step_equals_single_process(tmp_path, S, N, L, extra):
     import torch.multiprocessing as tmp
     import orc
     import rvh_b200 as rvh
     out = str(tmp_path / "sharded.npz")
-    tmp.spawn(_worker, args=(2, _free_port(), S, N, L, out), nprocs=2, join=True)
+    tmp.spawn(_worker, args=(2, _free_port(), S, N, L, extra, out), nprocs=2, join=True)
     z = np.load(out)
     dt = np.float32(1.0 / 60.0)
     cols = rvh.scenes.bench_colliders()
     st = rvh.scenes.synthetic_head(S, N, L, colliders=cols)
     rest = np.float32(L) / np.float32(N - 1)
-    p = orc.default_params(S, N, orc.GRID_ON | orc.WIND_B, rest_length=rest)
+    p = orc.default_params(S, N, orc.GRID_ON | orc.WIND_B | extra, rest_length=rest)
     for k in range(2):
         st, grid = orc.step(p, cols, dt, np.float32(0.25) + np.float32(k) * dt, st)
     assert np.array_equal(z["grid"], grid), "all-reduced grid differs from the single-process grid"
