@@ -613,10 +613,22 @@ __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const S
 template <int V> struct PackOf { using T = float2; static constexpr int n = V / 2; };
 template <> struct PackOf<1> { using T = float; static constexpr int n = 1; };
 
+// RVH_K1_STREAM_LOADS: the strand planes are read exactly once per step, so their loads can skip L1 allocation
+// (ld.global.nc.L1::no_allocate) and leave the cache to the gather's float grid, which neighbouring strands re-read.
+// Measured on B200 at 1M x 32: 0.338 vs 0.341 ms -- within noise, so it stays off.
+#ifndef RVH_K1_STREAM_LOADS
+#define RVH_K1_STREAM_LOADS 0
+#endif
 template <int V> __device__ __forceinline__ void load_packs(const float* __restrict__ p, typename PackOf<V>::T (&o)[PackOf<V>::n]) {
+#if RVH_K1_STREAM_LOADS
+    if constexpr (V == 1) { asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(o[0]) : "l"(p)); }
+    else if constexpr (V == 2) { asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(o[0].x), "=f"(o[0].y) : "l"(p)); }
+    else { asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0].x), "=f"(o[0].y), "=f"(o[1].x), "=f"(o[1].y) : "l"(p)); }
+#else
     if constexpr (V == 1) { o[0] = __ldg(p); }
     else if constexpr (V == 2) { o[0] = __ldg(reinterpret_cast<const float2*>(p)); }
     else { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); o[0] = make_float2(t.x, t.y); o[1] = make_float2(t.z, t.w); }
+#endif
 }
 template <int V> __device__ __forceinline__ void store_packs(float* __restrict__ p, const typename PackOf<V>::T (&o)[PackOf<V>::n]) {
     if constexpr (V == 1) { *p = o[0]; }
