@@ -104,3 +104,23 @@ def test_shard_ranges_partition_all_strands():
             r = [rvh.scenes.shard_range(S, k, R) for k in range(R)]
             assert r[0][0] == 0 and r[-1][1] == S
             assert all(r[i][1] == r[i + 1][0] for i in range(R - 1))
+
+
+def test_c_abi_is_usable_from_plain_c(tmp_path):
+    """include/rvh.h compiles as C11 and links against librvh.so; without a GPU the program must stop at rvh_create with the
+    no-fallback error (exit 3), with one it runs ten steps (exit 0)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(rvh.library_path())
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.check_call([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_smoke.c"),
+                           "-L", libdir, "-lrvh", "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert "abi 2" in out.stdout and "config 76 bytes" in out.stdout
+    if _has_gpu():
+        assert out.returncode == 0 and "10 steps ok" in out.stdout and "{900,1,0,0}" in out.stdout, out.stdout
+    else:
+        assert out.returncode == 3 and "no CPU fallback" in out.stdout, out.stdout
