@@ -106,7 +106,7 @@ def test_shard_ranges_partition_all_strands():
             assert all(r[i][1] == r[i + 1][0] for i in range(R - 1))
 
 
-def test_c_abi_is_usable_from_plain_c(tmp_path):
+def _c_abi_smoke(tmp_path):
     """include/rvh.h compiles as C11 and links against librvh.so; without a GPU the program must stop at rvh_create with the
     no-fallback error (exit 3), with one it runs ten steps (exit 0)."""
     import shutil
@@ -124,3 +124,13 @@ def test_c_abi_is_usable_from_plain_c(tmp_path):
         assert out.returncode == 0 and "10 steps ok" in out.stdout and "{900,1,0,0}" in out.stdout, out.stdout
     else:
         assert out.returncode == 3 and "no CPU fallback" in out.stdout, out.stdout
+
+
+def test_c_abi_is_usable_from_plain_c(tmp_path):
+    _c_abi_smoke(tmp_path)
+
+
+@pytest.mark.gpu
+def test_c_abi_smoke_runs_ten_steps_on_the_gpu(tmp_path):
+    assert _has_gpu()
+    _c_abi_smoke(tmp_path)
