@@ -42,7 +42,7 @@ def _worker(rank, world, uid, S, N, L, steps, out_dir, exchange):
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-@pytest.mark.parametrize("S,N,L", [(20000, 16, 0.4), (8192, 32, 2.5)])
+@pytest.mark.parametrize("S,N,L", [(20000, 16, 0.4), (8192, 32, 2.5), (600000, 8, 0.4)])      # the last one is wide enough for the fused grid clear and the collider mask
 def test_two_gpu_sharded_equals_one_gpu(tmp_path, S, N, L, exchange):
     import torch.multiprocessing as tmp
     import rvh_b200 as rvh
