@@ -134,3 +134,25 @@ def test_c_abi_is_usable_from_plain_c(tmp_path):
 def test_c_abi_smoke_runs_ten_steps_on_the_gpu(tmp_path):
     assert _has_gpu()
     _c_abi_smoke(tmp_path)
+
+
+def test_host_collider_maths_random_transforms_vs_oracle():
+    """Scene.h:28-38 for arbitrary translation / rotation (degrees) / scale: the library's own matrix code against the oracle's
+    glm restatement (which is pinned bit-exactly to the reference's glm build)."""
+    from hypothesis import given, settings, strategies as st
+    f = lambda lo, hi: st.floats(lo, hi, allow_nan=False, width=32)
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.tuples(f(-5, 5), f(-5, 5), f(-5, 5)), st.tuples(f(-180, 180), f(-180, 180), f(-180, 180)), st.tuples(f(0.25, 3), f(0.25, 3), f(0.25, 3)),
+           st.tuples(f(-2, 2), f(-2, 2), f(-2, 2)))
+    def check(t, r, s, move):
+        mine, ref = rvh.collider_build(t, r, s), orc.collider_build(t, r, s)
+        scale = np.abs(ref).max()
+        assert np.abs(mine - ref).max() <= 2e-5 * max(1.0, scale)              # inverse of a 0.25-scaled matrix has entries up to 4
+        # transform * inv == identity, invTrans == inv^T
+        X, I, IT = (mine[16 * k:16 * k + 16].reshape(4, 4).T.astype(np.float64) for k in range(3))
+        assert np.abs(X @ I - np.eye(4)).max() <= 1e-4
+        assert np.abs(IT - I.T).max() <= 1e-6
+        a, b = rvh.collider_translate(mine, move), orc.collider_translate(ref, move)
+        assert np.abs(a - b).max() <= 2e-5 * max(1.0, np.abs(b).max())
+    check()
