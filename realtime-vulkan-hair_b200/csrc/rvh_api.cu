@@ -61,7 +61,7 @@ struct rvh_ctx {
     float* corr = nullptr;                // [3][N][S_pad] (RVH_KEEP_CORRECTION)
     unsigned long long* grid = nullptr;   // [G^3][4] int64 accumulators
     float4* fgrid = nullptr;              // [G^3] float cells for the gather (k_grid_finalize)
-    int k1_blocks = 0, k1_launch_blocks = 0;   // CTAs of k_ftl_step for all strands / of the launch being issued
+    int k1_blocks = 0;
     uint4* k1_clear = nullptr; unsigned k1_clear_n = 0;    // grid clear fused into k_ftl_step (set per step)
     size_t grid_bytes = 0;
     int* perm = nullptr;                  // internal -> external strand index (Morton order)
@@ -74,16 +74,6 @@ struct rvh_ctx {
     StepParams P;
     bool uploaded = false, colliders_set = false;
     int splat_target_warps = 32768;       // RVH_SPLAT_WARPS env (tuning): the splat splits rows over blockIdx.y until it has this many warps
-    int splat_variant = 2;                // RVH_SPLAT_VARIANT env (experiments): 2 = 64-point rows, magic truncation (default), 1 = round-1 two-phase kernel, 0 = REDUX
-    // chunk-pipelined step: k_ftl_step of strand chunk j+1 on `stream` runs beside the splat of chunk j on `stream2`
-    cudaStream_t stream2 = nullptr;
-    std::vector<cudaEvent_t> chunk_ev;    // one per chunk: k_ftl_step of the chunk is done
-    cudaEvent_t ev_join = nullptr;        // the last splat is done
-    int pipe = 1, pipe_ctas_per_sm = 3;   // RVH_PIPE (0 off), RVH_PIPE_F: CTAs of k_ftl_step per SM and chunk (the rest of the SM is the splat's)
-    int num_sms = 148;
-    int fuse_splat = 0;                   // RVH_FUSE_SPLAT env: 1 = the splat rides in k_ftl_step when possible (2 strands per thread, magic truncation, no extension)
-    bool fuse_splat_now = false;          // this step's decision
-    bool splat_magic = false;             // grid_scale < 2^23: float->int by FADD.RZ magic (k_grid_splat2<true>)
     bool gather_pending = false;          // fgrid holds a finalized grid whose gather has not been applied to the velocities yet
     // head SDF (extension)
     float* sdf_dev = nullptr;             // [nz][ny][nxp] node values
@@ -200,17 +190,10 @@ int update_collider_mask(rvh_ctx* ctx, const float* colliders, int n) {
 template <int V, bool WIND, int NELL>
 void launch_k1(rvh_ctx* c, int gather) {
     // gather: 0 = none pending, 1 = friction, 2 = friction + repulsion (extension: V <= 2 only, see create_impl)
-    if (c->fuse_splat_now) {      // the splat rides in the kernel: k1_clear carries the accumulator grid
-        if constexpr (V == 2 && NELL >= -1) {
-            if (gather == 1) k_ftl_step<V, WIND, NELL, 1, true><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, reinterpret_cast<uint4*>(c->grid), 0u);
-            else if constexpr (NELL < 100) k_ftl_step<V, WIND, NELL, 0, true><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, reinterpret_cast<uint4*>(c->grid), 0u);
-        }
-        return;
-    }
     if (gather == 2) {
-        if constexpr (V <= 2) k_ftl_step<V, WIND, NELL, 2><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
-    } else if (gather == 1) k_ftl_step<V, WIND, NELL, 1><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
-    else if constexpr (NELL < 100) k_ftl_step<V, WIND, NELL, 0><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
+        if constexpr (V <= 2) k_ftl_step<V, WIND, NELL, 2><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
+    } else if (gather == 1) k_ftl_step<V, WIND, NELL, 1><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
+    else if constexpr (NELL < 100) k_ftl_step<V, WIND, NELL, 0><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
 }
 template <int V>
 void launch_k1_v(rvh_ctx* c, bool wind, int gather) {
@@ -230,45 +213,6 @@ void launch_k1_v(rvh_ctx* c, bool wind, int gather) {
     }
     if (wind) { if (five) launch_k1<V, true, 5>(c, gather); else launch_k1<V, true, -1>(c, gather); }
     else      { if (five) launch_k1<V, false, 5>(c, gather); else launch_k1<V, false, -1>(c, gather); }
-}
-
-// Splat of the strand range [strand0, strand0 + nstrands) (multiples of 256) on stream `st`.
-int launch_splat(rvh_ctx* ctx, int strand0, int nstrands, cudaStream_t st, bool split_rows) {
-    ctx->P.strand0 = strand0;
-    const int rows = ctx->N - 1;
-    if (ctx->splat_variant == 0) {
-        k_grid_splat_redux<<<nstrands / kSplatThreads, kSplatThreads, 0, st>>>(ctx->P, ctx->planes, ctx->grid);
-    } else {
-        // enough warps to fill 148 SMs several times over: split the rows when there are few strands
-        const int per_warp = ctx->splat_variant == 2 ? 64 : 32, warps = nstrands / per_warp;
-        int chunks = split_rows ? std::max(1, std::min(rows, (ctx->splat_target_warps + warps - 1) / warps)) : 1;
-        const int rpc = (rows + chunks - 1) / chunks;
-        chunks = (rows + rpc - 1) / rpc;
-        if (ctx->splat_variant == 2) {
-            if (ctx->splat_magic) k_grid_splat2<true><<<dim3(nstrands / (2 * kS2Threads), chunks), kS2Threads, 0, st>>>(ctx->P, ctx->planes, ctx->grid, rpc);
-            else                  k_grid_splat2<false><<<dim3(nstrands / (2 * kS2Threads), chunks), kS2Threads, 0, st>>>(ctx->P, ctx->planes, ctx->grid, rpc);
-        } else {
-            if (ctx->P.scale > 0.f && ctx->P.scale < 8388608.0f)
-                k_grid_splat<true><<<dim3(nstrands / kSplatThreads, chunks), kSplatThreads, 0, st>>>(ctx->P, ctx->planes, ctx->grid, rpc);
-            else
-                k_grid_splat<false><<<dim3(nstrands / kSplatThreads, chunks), kSplatThreads, 0, st>>>(ctx->P, ctx->planes, ctx->grid, rpc);
-        }
-    }
-    ctx->P.strand0 = 0;
-    ctx->launches += 1;
-    CU(cudaGetLastError());
-    return RVH_OK;
-}
-
-void launch_ftl(rvh_ctx* ctx, bool wind, int fused_gather, int cta0, int nctas) {
-    ctx->P.cta0 = cta0; ctx->k1_launch_blocks = nctas;
-    switch (ctx->V) {
-        case 4: launch_k1_v<4>(ctx, wind, fused_gather); break;
-        case 2: launch_k1_v<2>(ctx, wind, fused_gather); break;
-        default: launch_k1_v<1>(ctx, wind, fused_gather); break;
-    }
-    ctx->P.cta0 = 0;
-    ctx->launches += 1;
 }
 
 int launch_gather(rvh_ctx* ctx) {
@@ -318,14 +262,7 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
     if (phases & 1) {
         // Renderer.cpp:2063.  Wide launches clear the grid from inside k_ftl_step (<= 4 stores of 16 bytes per thread)
         const size_t clear_n = ctx->grid_bytes / 16;
-        const int fused_gather_kind = ctx->gather_pending ? ((flags & RVH_REPULSION_ON) ? 2 : 1) : 0;
-        ctx->fuse_splat_now = grid && ctx->fuse_splat && ctx->V == 2 && ctx->splat_magic && !(flags & RVH_SDF_ON) && fused_gather_kind != 2 && !ctx->corr;
-        // pipelined: at least two chunks of pipe_ctas_per_sm * SMs CTAs, chunk boundaries on layout tiles (V <= 2: a CTA covers 128 or 256 strands)
-        const int chunk_ctas = ctx->pipe_ctas_per_sm * ctx->num_sms;
-        const int nchunks = (ctx->k1_blocks + chunk_ctas - 1) / chunk_ctas;
-        const bool pipelined = grid && ctx->pipe && !ctx->fuse_splat_now && ctx->V == 2 && nchunks >= 2 && ctx->profiling != 1 && ctx->splat_variant != 0;
-        const bool fused_clear = grid && !ctx->fuse_splat_now && !pipelined && (size_t)ctx->k1_blocks * kBlock * 4 >= clear_n && clear_n < ((size_t)1 << 32) && !std::getenv("RVH_NO_FUSED_CLEAR");
-        if (pipelined) while ((int)ctx->chunk_ev.size() < nchunks) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+        const bool fused_clear = grid && (size_t)ctx->k1_blocks * kBlock * 4 >= clear_n && clear_n < ((size_t)1 << 32) && !std::getenv("RVH_NO_FUSED_CLEAR");
         ctx->k1_clear = fused_clear ? reinterpret_cast<uint4*>(ctx->grid) : nullptr;
         ctx->k1_clear_n = fused_clear ? (unsigned)clear_n : 0u;
         if (grid && !fused_clear) {
@@ -333,38 +270,33 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
             CU(cudaMemsetAsync(ctx->grid, 0, ctx->grid_bytes, ctx->stream));
             prof_end(ctx);
         }
-        const int fused_gather = fused_gather_kind;
-        if (pipelined) {
-            // chunk j+1's k_ftl_step (HBM/latency-bound, leaves issue slots idle) runs beside chunk j's splat (issue-bound): each
-            // k_ftl_step launch covers only pipe_ctas_per_sm CTAs per SM, so the splat's CTAs find room on every SM
-            const int per = (ctx->k1_blocks + nchunks - 1) / nchunks;
-            const int strands_per_cta = kBlock * ctx->V;
-            for (int j = 0; j < nchunks; ++j) {
-                const int c0 = j * per, nc = std::min(per, ctx->k1_blocks - c0);
-                if (nc <= 0) break;
-                if (j == 0) prof_begin(ctx, EV_K1);
-                launch_ftl(ctx, wind, fused_gather, c0, nc);
-                CU(cudaGetLastError());
-                if (c0 + nc >= ctx->k1_blocks) prof_end(ctx);
-                CU(cudaEventRecord(ctx->chunk_ev[j], ctx->stream));
-                CU(cudaStreamWaitEvent(ctx->stream2, ctx->chunk_ev[j], 0));
-                const int s0 = c0 * strands_per_cta, ns = std::min(nc * strands_per_cta, ctx->S_pad - s0);
-                { int r = launch_splat(ctx, s0, ns, ctx->stream2, false); if (r) return r; }
+        prof_begin(ctx, EV_K1);
+        const int fused_gather = ctx->gather_pending ? ((flags & RVH_REPULSION_ON) ? 2 : 1) : 0;
+        switch (ctx->V) {
+            case 4: launch_k1_v<4>(ctx, wind, fused_gather); break;
+            case 2: launch_k1_v<2>(ctx, wind, fused_gather); break;
+            default: launch_k1_v<1>(ctx, wind, fused_gather); break;
+        }
+        prof_end(ctx);
+        ctx->gather_pending = false;
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+        if (grid) {
+            prof_begin(ctx, EV_SPLAT);
+            {
+                // enough warps to fill 148 SMs several times over: split the rows when there are few strands
+                const int warps = ctx->S_pad / 32, rows = ctx->N - 1;
+                int chunks = std::max(1, std::min(rows, (ctx->splat_target_warps + warps - 1) / warps));
+                const int rpc = (rows + chunks - 1) / chunks;
+                chunks = (rows + rpc - 1) / rpc;
+                if (ctx->P.scale > 0.f && ctx->P.scale < 8388608.0f)
+                    k_grid_splat<true><<<dim3(ctx->S_pad / kSplatThreads, chunks), kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid, rpc);
+                else
+                    k_grid_splat<false><<<dim3(ctx->S_pad / kSplatThreads, chunks), kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid, rpc);
             }
-            CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
-            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-            ctx->gather_pending = false;
-        } else {
-            prof_begin(ctx, EV_K1);
-            launch_ftl(ctx, wind, fused_gather, 0, ctx->k1_blocks);
             prof_end(ctx);
-            ctx->gather_pending = false;
+            ctx->launches += 1;
             CU(cudaGetLastError());
-            if (grid && !ctx->fuse_splat_now) {
-                prof_begin(ctx, EV_SPLAT);
-                { int r = launch_splat(ctx, 0, ctx->S_pad, ctx->stream, true); if (r) return r; }
-                prof_end(ctx);
-            }
         }
         if (grid && ctx->nranks > 1) {
             ctx->grid_reduced = false;
@@ -456,7 +388,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     if (!out || !cfg) return fail(nullptr, RVH_ERR_INVALID, "null argument");
     *out = nullptr;
     if (cfg->num_strands < 1 || cfg->num_points < 2) return fail(nullptr, RVH_ERR_INVALID, "need num_strands >= 1 and num_points >= 2");
-    if (cfg->grid_dim < 2 || cfg->grid_dim > 1023) return fail(nullptr, RVH_ERR_INVALID, "grid_dim out of range (2..1023: the splat keys hold 10 bits per axis)");
+    if (cfg->grid_dim < 2 || cfg->grid_dim > 1023) return fail(nullptr, RVH_ERR_INVALID, "grid_dim out of range (2..1023: the splat's cell keys hold 10 bits per axis)");
     if ((size_t)cfg->num_strands * cfg->num_points > ((size_t)1 << 31)) return fail(nullptr, RVH_ERR_INVALID, "S*N too large for one context");
     if ((cfg->flags & RVH_REPULSION_ON) && !(cfg->flags & RVH_GRID_ON)) return fail(nullptr, RVH_ERR_INVALID, "RVH_REPULSION_ON needs RVH_GRID_ON (it reads the same voxel grid)");
     int ndev = 0;
@@ -471,8 +403,6 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->S = cfg->num_strands; c->N = cfg->num_points;
     c->S_pad = ((c->S + kTileStrands - 1) / kTileStrands) * kTileStrands;
     c->rank = rank; c->nranks = nranks;
-    if (const char* e = std::getenv("RVH_SPLAT_VARIANT")) c->splat_variant = std::atoi(e);
-    if (const char* e = std::getenv("RVH_FUSE_SPLAT")) c->fuse_splat = std::atoi(e);
     if (const char* e = std::getenv("RVH_SPLAT_WARPS")) c->splat_target_warps = std::max(1, std::atoi(e));
     int V = cfg->strands_per_thread;
     if (V != 1 && V != 2 && V != 4) V = c->S >= 65536 ? 2 : 1;     // measured on B200: 2 strands per thread is fastest at scale
@@ -499,11 +429,6 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->aos_bytes = (size_t)c->S * 48 * c->N;
     CUC(cudaMalloc(&c->aos_dev, c->aos_bytes));
     CUC(cudaEventCreate(&c->ev_a)); CUC(cudaEventCreate(&c->ev_b));
-    CUC(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    CUC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    { cudaDeviceProp prop; CUC(cudaGetDeviceProperties(&prop, cfg->device)); c->num_sms = prop.multiProcessorCount; }
-    if (const char* e = std::getenv("RVH_PIPE")) c->pipe = std::atoi(e);
-    if (const char* e = std::getenv("RVH_PIPE_F")) c->pipe_ctas_per_sm = std::max(1, std::atoi(e));
     CUC(cudaFuncSetAttribute(k_unpack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * c->N * (kTile + 1) * (int)sizeof(float)));
     CUC(cudaFuncSetAttribute(k_pack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * c->N * (kTile + 1) * (int)sizeof(float)));
 
@@ -523,18 +448,16 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     P.scale = cfg->grid_scale; P.friction = cfg->friction;
     P.repulsion = cfg->repulsion; P.inv_h = 1.0f / P.h;
     P.int32_wrap = (cfg->flags & RVH_GRID_INT32_WRAP) ? 1 : 0;
-    {   // k_grid_splat2's velocity bounds.  A staged point's contributions are RN(scale * RN(tw * |v|)) with tw <= 1, so they are
-        // bounded by RN(scale * |v|): magic truncation needs that < 2^23 (and scale itself, the density term, too); the int32
-        // accumulators take the 64 points of a row, so the aggregated path needs it < 2^25.  Above: one point at a time, 64-bit.
-        auto bound = [&](float lim) {
-            if (!(P.scale > 0.f) || !(P.scale < lim)) return -1.0f;
-            float v = lim / P.scale;
+    {   // k_grid_splat sums the 32 points of a row in int32 registers: a contribution is RN(scale * RN(tw * v)) with tw <= 1, bounded
+        // by RN(scale * |v|), and must stay below 2^26 (the density term, scale itself, too).  Faster points -- or every point when
+        // grid_scale is that large -- go to the grid one by one with 64-bit conversions (splat_point_direct).
+        const float lim = 67108863.0f;
+        float v = -1.0f;
+        if (P.scale > 0.f && P.scale < lim) {
+            v = lim / P.scale;
             while (v > 0.f && P.scale * v > lim) v = std::nextafterf(v, 0.f);
-            return v;
-        };
-        P.splat_vfast = bound(8388607.5f);
-        P.splat_vagg = bound(33554431.0f);
-        c->splat_magic = P.splat_vfast > 0.f;
+        }
+        P.splat_vagg = v;
     }
     P.keep_corr = c->corr ? 1 : 0;
 
@@ -1058,9 +981,6 @@ void rvh_destroy(rvh_ctx* c) {
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
-    for (cudaEvent_t e : c->chunk_ev) cudaEventDestroy(e);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -72,8 +72,7 @@ struct StepParams {
     int cmask_dim;                          // G / 2
     SdfVolume sdf;                          // RVH_SDF_ON
     float repulsion, inv_h;                 // RVH_REPULSION_ON: v -= repulsion * h*grad(rho)/sum(D) (gather_pack); inv_h = 1/h
-    int cta0, strand0;                      // chunked launches (pipelined step): first CTA of this k_ftl_step launch; first strand of this splat launch
-    float splat_vfast, splat_vagg;          // k_grid_splat2: |v| <= vfast: scale*|v| < 2^23 (magic truncation); |v| <= vagg: 64 such terms fit an int32
+    float splat_vagg;                       // k_grid_splat: points with |v|_inf <= splat_vagg are aggregated in int32 registers (32 contributions of <= 2^26 each)
 };
 
 // ---- wind trigonometry ---------------------------------------------------------------------------
@@ -153,8 +152,9 @@ __device__ __forceinline__ T grid_coord(const StepParams& P, T p, int axis) {
 template <class T> struct AxisCells { T w0, w1; int f[VecTraits<T>::n]; };
 __device__ __forceinline__ bool nan3(float x, float y, float z) { const float t = x + y + z; return !(t == t); }
 
-// CVT_FLOOR: f from one F2I.FLOOR + integer clamp (fewer XU operations: the splat is XU-bound) instead of
-// FRND.FLOOR + float clamp + F2I (fewer registers: the gather inside k_ftl_step is register-bound).  Same f.
+// CVT_FLOOR: f from one F2I.FLOOR + integer clamp instead of FRND.FLOOR + float clamp + F2I (fewer registers: the gather inside
+// k_ftl_step is register-bound).  Same f.  (Round 2: the magic-number floor k_grid_splat uses -- FADD.RM with 1.5*2^23 -- was tried
+// here too: fewer instructions, but 88 B of spills at 96 registers, k_ftl_step 0.343 -> 0.411 ms; at 128 registers no change.)
 template <class T, bool CVT_FLOOR>
 __device__ __forceinline__ AxisCells<T> axis_cells(const StepParams& P, T p, int axis) {
     constexpr int n = VecTraits<T>::n;
@@ -607,264 +607,6 @@ __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const S
     return o;
 }
 
-__device__ __noinline__ void splat_point_direct_cold(const StepParams& P, unsigned long long* __restrict__ grid, int fx, int fy, int fz,
-                                                     float wx0, float wx1, float wy0, float wy1, float wz0, float wz1, float vx, float vy, float vz) {
-    const float ax[2] = { wx0, wx1 }, ay[2] = { wy0, wy1 }, az[2] = { wz0, wz1 };
-    splat_point_direct(P, grid, fx, fy, fz, ax, ay, az, vx, vy, vz);
-}
-
-// ---- K_splat, 64-point rows ("splat2") -----------------------------------------------------------------
-// Same two-phase idea as k_grid_splat, rebuilt around what ncu showed it spends its issue slots on (profiles/r02_summary.md):
-//   * a thread owns TWO neighbouring strands, so phase A (grid coordinates, weights, key) runs on fp32x2 packs and a warp-row
-//     is 64 points: discovery and flush are amortised over twice the points;
-//   * floor() and every float->int truncation ride the FMA pipe as magic-number additions with a directed rounding mode
-//     (FADD2.RM / FADD2.RZ with 1.5*2^23 / 2^23: two results per instruction) instead of F2I / I2F on the quarter-rate XU
-//     pipe.  Truncation toward zero needs the sign: phase A stages |v| and sign(v) = +-1, phase B truncates the
-//     non-negative magnitude s*(tw*|v|) (round-to-nearest is symmetric, so it is the magnitude of the shader's s*(tw*v))
-//     and IMADs  bits * sign  into the accumulator; the 0x4B000000 exponent bias every such term carries is removed once per
-//     flushed value from ballot counts (B * (members - 2*negative members));
-//   * the row's base cells are known before phase B (REDUX.MIN/MAX over the keys), so the common rows take a loop without
-//     per-point key tests: one cell = unconditional adds; two / three cells = unconditional sum of ALL points plus one / two
-//     predicated sets, the last cell by subtraction.  Only rows that also hold excluded points (outside the grid, too fast)
-//     or more than three cells use fully predicated passes of up to three cells each.
-// Rows holding a point with |v| above splat_vfast (s*|v| would leave [0, 2^23)) convert with F2I instead; points above
-// splat_vagg (64 of them could overflow the int32 accumulators) go to the grid one by one in 64-bit.  Integer sums are exact
-// in any order, so the grid stays bit-identical to the shader's (and to k_grid_splat's).
-constexpr int kS2Threads = 128;            // 4 warps x 64 strands = one layout tile of 256 strands
-constexpr int kS2W = 68;                   // floats between the cell-f and cell-f+1 weight rows: distinct banks for LDS.128
-constexpr int kMagicBias = 0x4B000000;     // bits of 2^23
-
-struct __align__(16) Splat2Stage {         // one row of one warp: 64 points, point 2*lane + e
-    float w[3][2][kS2W];                   // [axis][cell f / f+1][point]
-    float u[3][64];                        // |v|
-    int sg[3][64];                         // sign(v): +1 / -1
-    int key[64];                           // base-cell key (f+1 per axis, 10 bits each), -1 = not aggregated
-};
-
-__device__ __forceinline__ float2 fadd2_rm(float2 a, float2 b) {
-    float2 r;
-    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r)) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return r;
-}
-__device__ __forceinline__ float2 fadd2_rz(float2 a, float2 b) {
-    float2 r;
-    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r)) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return r;
-}
-
-// truncation of a pack of non-negative values: MAGIC  -> bits of (x + 2^23) rounded toward zero = 0x4B000000 + floor(x) for x < 2^23
-//                                              !MAGIC -> F2I.TRUNC
-template <bool MAGIC>
-__device__ __forceinline__ int2 trunc_pack(float2 x) {
-    if (MAGIC) { const float2 r = fadd2_rz(x, make_float2(8388608.0f, 8388608.0f)); return make_int2(__float_as_int(r.x), __float_as_int(r.y)); }
-    return make_int2(__float2int_rz(x.x), __float2int_rz(x.y));
-}
-
-// One pass of phase B over the staged row.  lane = (corner, slot): the lane turns the (point, corner) pairs of its slot's 16
-// points into integers, two points per fp32x2 pack, and accumulates them
-//   ALL: into acc[0] unconditionally (every staged point is an aggregated point: no key load, no test), and
-//   NP : into acc[ALL + j] for the points whose key is K[j].
-template <bool MAGIC, int NP, bool ALL>
-__device__ __forceinline__ void splat2_pass(const Splat2Stage& st, float scale, int lane, const int (&K)[3], int (&acc)[4][4]) {
-    const int ca = lane & 1, cb = (lane >> 1) & 1, cc = (lane >> 2) & 1, slot = lane >> 3;
-    const float4* wx = reinterpret_cast<const float4*>(st.w[0][ca]) + slot;
-    const float4* wy = reinterpret_cast<const float4*>(st.w[1][cb]) + slot;
-    const float4* wz = reinterpret_cast<const float4*>(st.w[2][cc]) + slot;
-    const float4* ux = reinterpret_cast<const float4*>(st.u[0]) + slot;
-    const float4* uy = reinterpret_cast<const float4*>(st.u[1]) + slot;
-    const float4* uz = reinterpret_cast<const float4*>(st.u[2]) + slot;
-    const int4* sx = reinterpret_cast<const int4*>(st.sg[0]) + slot;
-    const int4* sy = reinterpret_cast<const int4*>(st.sg[1]) + slot;
-    const int4* sz = reinterpret_cast<const int4*>(st.sg[2]) + slot;
-    const int4* kp = reinterpret_cast<const int4*>(st.key) + slot;
-    const float2 sc2 = make_float2(scale, scale);
-#pragma unroll
-    for (int q = 0; q < NP + (ALL ? 1 : 0); ++q) { acc[q][0] = 0; acc[q][1] = 0; acc[q][2] = 0; acc[q][3] = 0; }
-#pragma unroll 2
-    for (int it = 0; it < 4; ++it) {
-        const int q4 = 4 * it;                                      // float4 index: points 16*it + 4*slot .. +3
-        const float4 WX = wx[q4], WY = wy[q4], WZ = wz[q4], UX = ux[q4], UY = uy[q4], UZ = uz[q4];
-        const int4 SX = sx[q4], SY = sy[q4], SZ = sz[q4];
-        int4 KK = make_int4(0, 0, 0, 0);
-        if (NP > 0) KK = kp[q4];
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            const float2 w0 = hf ? make_float2(WX.z, WX.w) : make_float2(WX.x, WX.y);
-            const float2 w1 = hf ? make_float2(WY.z, WY.w) : make_float2(WY.x, WY.y);
-            const float2 w2 = hf ? make_float2(WZ.z, WZ.w) : make_float2(WZ.x, WZ.y);
-            const float2 tw = __fmul2_rn(__fmul2_rn(w0, w1), w2);                                  // compute.comp:241-243
-            const float2 mx = __fmul2_rn(sc2, __fmul2_rn(tw, hf ? make_float2(UX.z, UX.w) : make_float2(UX.x, UX.y)));   // |SCALE * (w * v)|, :245-247
-            const float2 my = __fmul2_rn(sc2, __fmul2_rn(tw, hf ? make_float2(UY.z, UY.w) : make_float2(UY.x, UY.y)));
-            const float2 mz = __fmul2_rn(sc2, __fmul2_rn(tw, hf ? make_float2(UZ.z, UZ.w) : make_float2(UZ.x, UZ.y)));
-            const float2 md = __fmul2_rn(sc2, tw);                                                 // :248
-            const int2 bx = trunc_pack<MAGIC>(mx), by = trunc_pack<MAGIC>(my), bz = trunc_pack<MAGIC>(mz), bd = trunc_pack<MAGIC>(md);
-            const int s0x = hf ? SX.z : SX.x, s1x = hf ? SX.w : SX.y, s0y = hf ? SY.z : SY.x, s1y = hf ? SY.w : SY.y, s0z = hf ? SZ.z : SZ.x, s1z = hf ? SZ.w : SZ.y;
-            if (ALL) {
-                acc[0][0] = bx.y * s1x + (bx.x * s0x + acc[0][0]);
-                acc[0][1] = by.y * s1y + (by.x * s0y + acc[0][1]);
-                acc[0][2] = bz.y * s1z + (bz.x * s0z + acc[0][2]);
-                acc[0][3] += bd.x + bd.y;
-            }
-            const int k0 = hf ? KK.z : KK.x, k1 = hf ? KK.w : KK.y;
-#pragma unroll
-            for (int j = 0; j < NP; ++j) {
-                int (&a)[4] = acc[(ALL ? 1 : 0) + j];
-                if (k0 == K[j]) { a[0] = bx.x * s0x + a[0]; a[1] = by.x * s0y + a[1]; a[2] = bz.x * s0z + a[2]; a[3] += bd.x; }
-                if (k1 == K[j]) { a[0] = bx.y * s1x + a[0]; a[1] = by.y * s1y + a[1]; a[2] = bz.y * s1z + a[2]; a[3] += bd.y; }
-            }
-        }
-    }
-}
-
-// The accumulators of ONE cell -> grid.  Sum over the 4 slots of each corner so that every lane ends up with one component of
-// its corner (12-instruction reduce-scatter), take off the magic bias of the set's members, one RED.64 per lane.
-// ma / mb: ballots of the set's members among points 2*lane / 2*lane+1; nb: ballots of the negative signs [component][e].
-template <bool MAGIC>
-__device__ __forceinline__ void splat2_flush(const StepParams& P, unsigned long long* __restrict__ grid, int lane, int key, const int (&a)[4],
-                                             unsigned ma, unsigned mb, const unsigned (&nb)[3][2]) {
-    constexpr unsigned kFull = 0xffffffffu;
-    const bool hi = lane & 16, mid = lane & 8;
-    int k0 = hi ? a[2] : a[0], k1 = hi ? a[3] : a[1];
-    k0 += __shfl_xor_sync(kFull, hi ? a[0] : a[2], 16);
-    k1 += __shfl_xor_sync(kFull, hi ? a[1] : a[3], 16);
-    int mine = mid ? k1 : k0;
-    mine += __shfl_xor_sync(kFull, mid ? k0 : k1, 8);
-    const int comp = (hi ? 2 : 0) + (mid ? 1 : 0);
-    if (MAGIC) {
-        const int cnt = __popc(ma) + __popc(mb);
-        const unsigned na = comp == 0 ? nb[0][0] : (comp == 1 ? nb[1][0] : nb[2][0]), nbb = comp == 0 ? nb[0][1] : (comp == 1 ? nb[1][1] : nb[2][1]);
-        const int neg = comp == 3 ? 0 : __popc(ma & na) + __popc(mb & nbb);
-        mine -= kMagicBias * (cnt - 2 * neg);                       // modulo 2^32, like the accumulation itself
-    }
-    const int fx = (key & 1023) - 1 + (lane & 1), fy = ((key >> 10) & 1023) - 1 + ((lane >> 1) & 1), fz = (key >> 20) - 1 + ((lane >> 2) & 1);
-    if (cell_ok(fx, P.G) && cell_ok(fy, P.G) && cell_ok(fz, P.G))
-        global_add(grid + 4 * (size_t)(fx + (fy + fz * P.G) * P.G) + comp, (long long)mine);
-}
-
-// One warp-row: the 64 points (2 per lane, packs in .x/.y) -> grid.  Whole warp, converged.
-template <bool MAGIC>
-__device__ __forceinline__ void splat2_row(const StepParams& P, unsigned long long* __restrict__ grid, Splat2Stage& st, int lane, bool live0, bool live1,
-                                           float2 px, float2 py, float2 pz, float2 vx, float2 vy, float2 vz) {
-    constexpr unsigned kFull = 0xffffffffu;
-    // ---- phase A: lane = two strands ------------------------------------------------------------------------
-    // floor(g) as a float and as an integer from ONE directed-rounding addition: t = RM(g + 1.5*2^23) = 1.5*2^23 + floor(g) for
-    // |g| < 2^22, so fl = t - 1.5*2^23 and bits(t) - 0x4B3FFFFF = floor(g) + 1.  bits(t) is monotonic in g, hence
-    // "0 <= floor(g)+1 <= G" holds for exactly the g in [-1, G), NaN and far-away points included: no clamp, no F2I, no I2F.
-    const float2 M2 = make_float2(12582912.0f, 12582912.0f);
-    const float2 p3[3] = { px, py, pz };
-    int f1[3][2];
-    bool ok0 = live0, ok1 = live1;
-    float2 w0[3], w1[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float2 g = grid_coord<float2>(P, p3[a], a);
-        const float2 t = fadd2_rm(g, M2);
-        const float2 fl = vsub(t, M2);
-        f1[a][0] = __float_as_int(t.x) - 0x4B3FFFFF; f1[a][1] = __float_as_int(t.y) - 0x4B3FFFFF;
-        ok0 = ok0 && (unsigned)f1[a][0] <= (unsigned)P.G;           // some corner is a cell  <=>  -1 <= f <= G-1 on every axis
-        ok1 = ok1 && (unsigned)f1[a][1] <= (unsigned)P.G;
-        w0[a] = vfma(vsub(g, fl), bc<float2>(-1.0f), bc<float2>(1.0f));
-        w1[a] = vadd(vsub(g, vadd(fl, bc<float2>(1.0f))), bc<float2>(1.0f));
-    }
-    const float vi0 = fmaxf(fabsf(vx.x), fmaxf(fabsf(vy.x), fabsf(vz.x))), vi1 = fmaxf(fabsf(vx.y), fmaxf(fabsf(vy.y), fabsf(vz.y)));
-    const bool agg0 = ok0 && vi0 <= P.splat_vagg, agg1 = ok1 && vi1 <= P.splat_vagg;       // a NaN velocity fails the test
-    if (ok0 && !agg0)                                               // very fast (or NaN) point: 64-bit path, on its own
-        splat_point_direct_cold(P, grid, f1[0][0] - 1, f1[1][0] - 1, f1[2][0] - 1, w0[0].x, w1[0].x, w0[1].x, w1[1].x, w0[2].x, w1[2].x, vx.x, vy.x, vz.x);
-    if (ok1 && !agg1)
-        splat_point_direct_cold(P, grid, f1[0][1] - 1, f1[1][1] - 1, f1[2][1] - 1, w0[0].y, w1[0].y, w0[1].y, w1[1].y, w0[2].y, w1[2].y, vx.y, vy.y, vz.y);
-    const unsigned b0 = __ballot_sync(kFull, agg0), b1 = __ballot_sync(kFull, agg1);
-    if ((b0 | b1) == 0u) return;                                    // nothing of this row is aggregated (warp-uniform)
-    const int key0 = agg0 ? (f1[0][0] | (f1[1][0] << 10) | (f1[2][0] << 20)) : -1;
-    const int key1 = agg1 ? (f1[0][1] | (f1[1][1] << 10) | (f1[2][1] << 20)) : -1;
-    const bool magic_row = MAGIC && !__any_sync(kFull, (agg0 && vi0 > P.splat_vfast) || (agg1 && vi1 > P.splat_vfast));
-    const bool all_in = (b0 & b1) == kFull;                         // every staged point is an aggregated point
-    __syncwarp();                                                   // the previous row's phase B is done with the stage
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        *reinterpret_cast<float2*>(&st.w[a][0][2 * lane]) = w0[a];
-        *reinterpret_cast<float2*>(&st.w[a][1][2 * lane]) = w1[a];
-    }
-    const float2 v3[3] = { vx, vy, vz };
-    unsigned nb[3][2];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        *reinterpret_cast<float2*>(&st.u[k][2 * lane]) = make_float2(fabsf(v3[k].x), fabsf(v3[k].y));
-        const bool n0 = agg0 && v3[k].x < 0.0f, n1 = agg1 && v3[k].y < 0.0f;              // excluded points count as +: they enter no set
-        *reinterpret_cast<int2*>(&st.sg[k][2 * lane]) = make_int2(n0 ? -1 : 1, n1 ? -1 : 1);
-        nb[k][0] = __ballot_sync(kFull, n0); nb[k][1] = __ballot_sync(kFull, n1);
-    }
-    *reinterpret_cast<int2*>(&st.key[2 * lane]) = make_int2(key0, key1);
-    __syncwarp();
-    // ---- the row's base cells, ascending -----------------------------------------------------------------------
-    const unsigned u0 = (unsigned)key0, u1 = (unsigned)key1;        // -1 = 0xffffffff: never the minimum while a key is left
-    const int kmax = __reduce_max_sync(kFull, max(key0, key1));
-    unsigned below = 0u;                                            // keys <= `below - 1` are done (0: none yet)
-    bool first = true;
-    for (;;) {
-        int K[3] = { -2, -2, -2 };
-        unsigned ma[3] = { 0u, 0u, 0u }, mb[3] = { 0u, 0u, 0u };
-        int nk = 0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            if (j > 0 && K[j - 1] == kmax) break;
-            const unsigned c0 = u0 >= below ? u0 : 0xffffffffu, c1 = u1 >= below ? u1 : 0xffffffffu;
-            const unsigned kj = __reduce_min_sync(kFull, min(c0, c1));
-            K[j] = (int)kj;
-            ma[j] = __ballot_sync(kFull, key0 == K[j]); mb[j] = __ballot_sync(kFull, key1 == K[j]);
-            below = kj + 1u;
-            nk = j + 1;
-        }
-        const bool last = (nk == 1 ? K[0] : (nk == 2 ? K[1] : K[2])) == kmax;
-        int acc[4][4];
-        if (first && last && all_in) {
-            // ---- 1..3 cells, no excluded point: sum of ALL points + (nk - 1) predicated sets, the last cell by subtraction
-            if (magic_row) {
-                if (nk == 1) splat2_pass<true, 0, true>(st, P.scale, lane, K, acc);
-                else if (nk == 2) splat2_pass<true, 1, true>(st, P.scale, lane, K, acc);
-                else splat2_pass<true, 2, true>(st, P.scale, lane, K, acc);
-            } else {
-                if (nk == 1) splat2_pass<false, 0, true>(st, P.scale, lane, K, acc);
-                else if (nk == 2) splat2_pass<false, 1, true>(st, P.scale, lane, K, acc);
-                else splat2_pass<false, 2, true>(st, P.scale, lane, K, acc);
-            }
-            unsigned ra = kFull, rb = kFull;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (j + 1 < nk) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[0][q] -= acc[1 + j][q];
-                    ra &= ~ma[j]; rb &= ~mb[j];
-                    if (magic_row) splat2_flush<true>(P, grid, lane, K[j], acc[1 + j], ma[j], mb[j], nb);
-                    else splat2_flush<false>(P, grid, lane, K[j], acc[1 + j], ma[j], mb[j], nb);
-                }
-            }
-            const int klast = nk == 1 ? K[0] : (nk == 2 ? K[1] : K[2]);
-            if (magic_row) splat2_flush<true>(P, grid, lane, klast, acc[0], ra, rb, nb);
-            else splat2_flush<false>(P, grid, lane, klast, acc[0], ra, rb, nb);
-        } else {
-            // ---- general: up to three cells per pass, every add behind its key test ----------------------------------
-            if (magic_row) {
-                if (nk == 1) splat2_pass<true, 1, false>(st, P.scale, lane, K, acc);
-                else if (nk == 2) splat2_pass<true, 2, false>(st, P.scale, lane, K, acc);
-                else splat2_pass<true, 3, false>(st, P.scale, lane, K, acc);
-            } else {
-                if (nk == 1) splat2_pass<false, 1, false>(st, P.scale, lane, K, acc);
-                else if (nk == 2) splat2_pass<false, 2, false>(st, P.scale, lane, K, acc);
-                else splat2_pass<false, 3, false>(st, P.scale, lane, K, acc);
-            }
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                if (j < nk) {
-                    if (magic_row) splat2_flush<true>(P, grid, lane, K[j], acc[j], ma[j], mb[j], nb);
-                    else splat2_flush<false>(P, grid, lane, K[j], acc[j], ma[j], mb[j], nb);
-                }
-            }
-        }
-        if (last) break;
-        first = false;
-    }
-}
-
 // ---- K1: integrate + collide + FTL + corrected velocity -------------------------------------
 // One thread owns V consecutive strands and walks them root->tip together.  V = 1: scalar; V = 2, 4:
 // strands are paired into fp32x2 packs (LDG.64 / LDG.128 deliver the packs directly).  Point i's
@@ -953,32 +695,21 @@ __device__ __forceinline__ void sdf_stage_row(const StepParams& P, const CUtenso
     }
 }
 
-// SPLAT (V = 2 only): the grid splat of compute.comp:231-252 rides in the same kernel.  Point i-1 is final (position AND
-// corrected velocity) once point i has been updated, so the warp hands its 64 points of row i-1 to splat2_row right there, out
-// of registers: the splat's 24 B/point re-read of what this kernel has just written, its address arithmetic and its launch
-// disappear, and its integer work fills the issue slots this HBM-bound kernel leaves idle.  `grid_clear` is then the
-// accumulator grid itself (cleared by the caller beforehand) and grid_clear_n = 0.
-#ifndef RVH_K1S_MINBLOCKS
-#define RVH_K1S_MINBLOCKS 4
-#endif
-template <int V, bool WIND, int NELL, int GATHER, bool SPLAT = false>
-__global__ void __launch_bounds__(kBlock, SPLAT ? RVH_K1S_MINBLOCKS : ((NELL <= -2 || GATHER == 2) ? RVH_K1X_MINBLOCKS : (GATHER ? RVH_K1G_MINBLOCKS : RVH_K1_MINBLOCKS)))
+template <int V, bool WIND, int NELL, int GATHER>
+__global__ void __launch_bounds__(kBlock, (NELL <= -2 || GATHER == 2) ? RVH_K1X_MINBLOCKS : (GATHER ? RVH_K1G_MINBLOCKS : RVH_K1_MINBLOCKS))
 k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr,
            const float4* __restrict__ fgrid, const __grid_constant__ CUtensorMap sdf_map, uint4* __restrict__ grid_clear, unsigned grid_clear_n) {
     using T = typename PackOf<V>::T;
     constexpr int NP = PackOf<V>::n;
     constexpr bool TMA = NELL == -3;
-    static_assert(!SPLAT || (V == 2 && !TMA), "the fused splat works on the fp32x2 packs of two strands per thread");
-    __shared__ Splat2Stage sstage[SPLAT ? kBlock / 32 : 1];
-    unsigned long long* const sgrid = reinterpret_cast<unsigned long long*>(grid_clear);
     // The step's grid clear (Renderer.cpp:2063) rides here when the launch is wide enough: this kernel never touches the
     // int64 accumulators (it reads the float grid), the splat that fills them comes after it in the stream, and whoever
     // read them last (finalize / exchange / a download) came before it.  Saves the memset launch.
-    if (!SPLAT && grid_clear)
+    if (grid_clear)
         for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < grid_clear_n; k += gridDim.x * blockDim.x) grid_clear[k] = make_uint4(0u, 0u, 0u, 0u);
     __shared__ __align__(128) unsigned char sdf_raw[TMA ? sizeof(SdfStageSmem) : 16];
     SdfStageSmem& sm = *reinterpret_cast<SdfStageSmem*>(sdf_raw);
-    const int t = (P.cta0 + blockIdx.x) * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int s0 = t * V;
     if (!TMA && s0 >= P.S_pad) return;                            // TMA variant: S_pad is a multiple of kBlock*V (V <= 2), no partial CTA
     const size_t RS = (size_t)P.S_pad * 6;                      // elements per row (all tiles, six planes)
@@ -1037,11 +768,9 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
             phase ^= 1u << b;
         }
         T fvx[NP], fvy[NP], fvz[NP], odx[NP], ody[NP], odz[NP];
-        T qx[NP], qy[NP], qz[NP];                                 // SPLAT: final position of point i-1
 #pragma unroll
         for (int u = 0; u < NP; ++u) {
             const PointOut<T> o = point_update<T, WIND, NELL, GATHER>(P, tile, fgrid, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
-            qx[u] = parx[u]; qy[u] = pary[u]; qz[u] = parz[u];
             parx[u] = o.px; pary[u] = o.py; parz[u] = o.pz;
             odx[u] = o.dx; ody[u] = o.dy; odz[u] = o.dz;
             // finalise point i-1: v_{i-1} -= d_i / dt   (compute.comp:213-215)
@@ -1055,13 +784,9 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
         }
         if (i > 1) { store_packs<V>(prevp + 3 * PK, fvx); store_packs<V>(prevp + 4 * PK, fvy); store_packs<V>(prevp + 5 * PK, fvz); }
         prevp = curp;
-        if constexpr (SPLAT) {
-            if (i > 1) splat2_row<true>(P, sgrid, sstage[wid], threadIdx.x & 31, s0 < P.S, s0 + 1 < P.S, qx[0], qy[0], qz[0], fvx[0], fvy[0], fvz[0]);
-        }
     }
     // last point: no correction term (compute.comp:213 `i != NUM_CURVE_POINTS - 1`)
     store_packs<V>(prevp + 3 * PK, lvx); store_packs<V>(prevp + 4 * PK, lvy); store_packs<V>(prevp + 5 * PK, lvz);
-    if constexpr (SPLAT) splat2_row<true>(P, sgrid, sstage[wid], threadIdx.x & 31, s0 < P.S, s0 + 1 < P.S, parx[0], pary[0], parz[0], lvx[0], lvy[0], lvz[0]);
 }
 
 // ---- K_splat: corrected velocities -> voxel grid (compute.comp:231-252) ----------------------------
@@ -1084,18 +809,16 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
 #endif
 
 constexpr int kSplatThreads = RVH_SPLAT_THREADS;
-constexpr float kSplatAggVmax = 60.0f;    // |c| <= 6e7 per contribution, 8 per lane, 4 lanes per corner: < 2^31
-constexpr int kStageW = 40;                // words between the a=0 and a=1 weight rows: distinct banks for LDS.64
+constexpr int kStageW = 40;                // words between the a=0 and a=1 weight rows: distinct banks for the quarter-warp phases of LDS.128
 
-struct SplatStage {                        // one row of one warp
+struct __align__(16) SplatStage {          // one row of one warp
     float w[3][2][kStageW];                // [axis][cell f / f+1][point]
     float v[3][32];                        // [component][point]
     int key[32];                           // base-cell key, -1 = nothing to add
 };
 
-__device__ __forceinline__ int splat_key(int fx, int fy, int fz) {       // f in [-2, G], G <= 1024: 11 bits each
-    return (fx + 2) | ((fy + 2) << 11) | ((fz + 2) << 22);
-}
+// f+1 per axis in [0, G], G <= 1023: 10 bits each, always a non-negative int
+__device__ __forceinline__ int splat_key(int f1x, int f1y, int f1z) { return f1x | (f1y << 10) | (f1z << 20); }
 
 // Sum the accumulators of one cell over the 4 slots of each corner (lanes l, l^8, l^16, l^24) so that the lane
 // ends up with ONE component of its corner, then add it to the grid: one RED.64 per lane, 32 distinct addresses.
@@ -1109,22 +832,45 @@ __device__ __forceinline__ void splat_flush_cell(const StepParams& P, unsigned l
     int mine = mid ? k1 : k0;
     mine += __shfl_xor_sync(kFull, mid ? k0 : k1, 8);
     const int comp = (hi ? 2 : 0) + (mid ? 1 : 0);
-    const int fx = (key & 2047) - 2 + (lane & 1), fy = ((key >> 11) & 2047) - 2 + ((lane >> 1) & 1), fz = (key >> 22) - 2 + ((lane >> 2) & 1);
+    const int fx = (key & 1023) - 1 + (lane & 1), fy = ((key >> 10) & 1023) - 1 + ((lane >> 1) & 1), fz = (key >> 20) - 1 + ((lane >> 2) & 1);
     if (cell_ok(fx, P.G) && cell_ok(fy, P.G) && cell_ok(fz, P.G))
         global_add(grid + 4 * (size_t)(fx + (fy + fz * P.G) * P.G) + comp, (long long)mine);
+}
+
+// the four integers of one (point, corner) pack: float operations ordered exactly as the shader orders them (compute.comp:241-248)
+template <bool MAGIC>
+__device__ __forceinline__ void splat_pack_ints(float2 sc2, float2 wx, float2 wy, float2 wz, float2 vx, float2 vy, float2 vz,
+                                                int2& ix, int2& iy, int2& iz, int2& id) {
+    const float2 tw = __fmul2_rn(__fmul2_rn(wx, wy), wz);
+    const float2 cx = __fmul2_rn(sc2, __fmul2_rn(tw, vx));
+    const float2 cy = __fmul2_rn(sc2, __fmul2_rn(tw, vy));
+    const float2 cz = __fmul2_rn(sc2, __fmul2_rn(tw, vz));
+    const float2 cd = __fmul2_rn(sc2, tw);
+    ix = make_int2(__float2int_rz(cx.x), __float2int_rz(cx.y));
+    iy = make_int2(__float2int_rz(cy.x), __float2int_rz(cy.y));
+    iz = make_int2(__float2int_rz(cz.x), __float2int_rz(cz.y));
+    if (MAGIC) {                                                   // 0 <= SCALE*w < 2^23: FADD.RZ with 2^23 on the FMA pipe, bias taken off by the caller's constant
+        id = make_int2(__float_as_int(__fadd_rz(cd.x, 8388608.0f)) - 0x4B000000, __float_as_int(__fadd_rz(cd.y, 8388608.0f)) - 0x4B000000);
+    } else id = make_int2(__float2int_rz(cd.x), __float2int_rz(cd.y));
 }
 
 // Rows are independent in the splat (unlike the FTL chain), so blockIdx.y splits them into chunks of
 // `rows_per_chunk`: scenes with few strands (C3: 100K x 64 = 3,125 warps walking 63 rows) still fill the machine.
 // MAGIC (host: grid_scale < 2^23): the density term 0 <= SCALE*w < 2^23 is truncated by FADD.RZ with 2^23 on the FMA pipe
 // instead of F2I on the quarter-rate XU pipe (same integer; splat 0.478 -> 0.460 ms at 1M x 32).
+// Round 2: floor(g) as float AND integer from one FADD.RM with 1.5*2^23 (no F2I / I2F / clamps in phase A); LDS.128 in
+// phase B (four points per load); rows whose 32 points share one base cell (about half of them) take a loop without
+// key loads, key tests or predicated adds (IADD3 sums both points of a pack).
+#ifndef RVH_SPLAT_MINBLOCKS
+#define RVH_SPLAT_MINBLOCKS 8
+#endif
 template <bool MAGIC>
-__global__ void __launch_bounds__(kSplatThreads)
+__global__ void __launch_bounds__(kSplatThreads, RVH_SPLAT_MINBLOCKS)
 k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid, int rows_per_chunk) {
     constexpr unsigned kFull = 0xffffffffu;
-    __shared__ __align__(16) SplatStage stage[kSplatThreads / 32][2];
+    __shared__ SplatStage stage[kSplatThreads / 32][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s = P.strand0 + blockIdx.x * kSplatThreads + threadIdx.x;   // S_pad is a multiple of 128: always in bounds
+    const int s = blockIdx.x * kSplatThreads + threadIdx.x;            // S_pad is a multiple of 128: always in bounds
     const bool live = s < P.S;
     if (!__any_sync(kFull, live)) return;
     const int r0 = 1 + blockIdx.y * rows_per_chunk, r1 = min(P.N, r0 + rows_per_chunk);
@@ -1146,187 +892,91 @@ k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ pla
             for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
         }
         // ---- phase A: lane = strand -------------------------------------------------------------------
-        const AxisCells<float> X = axis_cells<float, true>(P, c[0], 0), Y = axis_cells<float, true>(P, c[1], 1), Z = axis_cells<float, true>(P, c[2], 2);
-        // some corner is a cell  <=>  -1 <= f <= G-1 on every axis
-        const bool touches = live && cell_ok(X.f[0] + 1, P.G + 1) && cell_ok(Y.f[0] + 1, P.G + 1) && cell_ok(Z.f[0] + 1, P.G + 1) && !nan3(c[0], c[1], c[2]);
-        const float vinf = fmaxf(fabsf(c[3]), fmaxf(fabsf(c[4]), fabsf(c[5])));
-        int key = (touches && vinf <= kSplatAggVmax) ? splat_key(X.f[0], Y.f[0], Z.f[0]) : -1;
-        if (touches && key == -1) {                                     // very fast (or NaN) point: 64-bit path, on its own
-            const float wx[2] = { X.w0, X.w1 }, wy[2] = { Y.w0, Y.w1 }, wz[2] = { Z.w0, Z.w1 };
-            splat_point_direct(P, grid, X.f[0], Y.f[0], Z.f[0], wx, wy, wz, c[3], c[4], c[5]);
+        // t = RM(g + 1.5*2^23) = 1.5*2^23 + floor(g) for |g| < 2^22: fl = t - 1.5*2^23 is floor(g) as a float and
+        // bits(t) - 0x4B3FFFFF is floor(g) + 1 as an integer.  bits(t) is monotonic in g, so "0 <= floor(g)+1 <= G" holds for
+        // exactly the g in [-1, G) -- far-away and NaN coordinates included -- and some corner is a cell <=> it holds on every axis.
+        int f1[3]; float w0[3], w1[3];
+        bool touches = live;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float g = grid_coord<float>(P, c[a], a);
+            const float t = __fadd_rd(g, 12582912.0f);
+            const float fl = __fsub_rn(t, 12582912.0f);
+            f1[a] = __float_as_int(t) - 0x4B3FFFFF;
+            touches = touches && (unsigned)f1[a] <= (unsigned)P.G;
+            w0[a] = fmaf(__fsub_rn(g, fl), -1.0f, 1.0f);
+            w1[a] = __fadd_rn(__fsub_rn(g, __fadd_rn(fl, 1.0f)), 1.0f);
         }
-        unsigned rem = __ballot_sync(kFull, key != -1);
+        const float vinf = fmaxf(fabsf(c[3]), fmaxf(fabsf(c[4]), fabsf(c[5])));
+        const bool agg = touches && vinf <= P.splat_vagg;             // a NaN velocity fails the test
+        const int key = agg ? splat_key(f1[0], f1[1], f1[2]) : -1;
+        if (touches && !agg) {                                          // very fast (or NaN) point: 64-bit path, on its own
+            const float wx[2] = { w0[0], w1[0] }, wy[2] = { w0[1], w1[1] }, wz[2] = { w0[2], w1[2] };
+            splat_point_direct(P, grid, f1[0] - 1, f1[1] - 1, f1[2] - 1, wx, wy, wz, c[3], c[4], c[5]);
+        }
+        unsigned rem = __ballot_sync(kFull, agg);
         if (rem == 0u) continue;                                        // nothing of this row lands in the grid (warp-uniform)
         SplatStage& st = stage[warp][r & 1];
-        st.w[0][0][lane] = X.w0; st.w[0][1][lane] = X.w1; st.w[1][0][lane] = Y.w0; st.w[1][1][lane] = Y.w1;
-        st.w[2][0][lane] = Z.w0; st.w[2][1][lane] = Z.w1;
+        st.w[0][0][lane] = w0[0]; st.w[0][1][lane] = w1[0]; st.w[1][0][lane] = w0[1]; st.w[1][1][lane] = w1[1];
+        st.w[2][0][lane] = w0[2]; st.w[2][1][lane] = w1[2];
         st.v[0][lane] = c[3]; st.v[1][lane] = c[4]; st.v[2][lane] = c[5];
         st.key[lane] = key;
         __syncwarp();
-        // ---- phase B: lane = (corner, slot); pack = points (8*it + 2*slot, +1) ----------------------------
-        // two cells of the row per pass (one pass is the rule; a row that straddles more cells takes another)
-        while (rem) {
+        // ---- phase B: lane = (corner, slot); the slot's 8 points in two LDS.128 rounds of two fp32x2 packs -------------
+        const float4* wxp = reinterpret_cast<const float4*>(st.w[0][ca]) + slot;
+        const float4* wyp = reinterpret_cast<const float4*>(st.w[1][cb]) + slot;
+        const float4* wzp = reinterpret_cast<const float4*>(st.w[2][cc]) + slot;
+        const float4* vxp = reinterpret_cast<const float4*>(st.v[0]) + slot;
+        const float4* vyp = reinterpret_cast<const float4*>(st.v[1]) + slot;
+        const float4* vzp = reinterpret_cast<const float4*>(st.v[2]) + slot;
+        const int4* kp = reinterpret_cast<const int4*>(st.key) + slot;
         const int K0 = __shfl_sync(kFull, key, __ffs(rem) - 1);
-        rem &= ~__ballot_sync(kFull, key == K0);
-        int K1 = -1;
-        if (rem) { K1 = __shfl_sync(kFull, key, __ffs(rem) - 1); rem &= ~__ballot_sync(kFull, key == K1); }
-        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;          // cell K0
-        int e0 = 0, e1 = 0, e2 = 0, e3 = 0;          // cell K1
-        const float2* wxp = reinterpret_cast<const float2*>(st.w[0][ca]);
-        const float2* wyp = reinterpret_cast<const float2*>(st.w[1][cb]);
-        const float2* wzp = reinterpret_cast<const float2*>(st.w[2][cc]);
-        const float2* vxp = reinterpret_cast<const float2*>(st.v[0]);
-        const float2* vyp = reinterpret_cast<const float2*>(st.v[1]);
-        const float2* vzp = reinterpret_cast<const float2*>(st.v[2]);
-        const int2* kp = reinterpret_cast<const int2*>(st.key);
+        if (rem == kFull && __all_sync(kFull, key == K0)) {
+            // one base cell, every point aggregated (about half of all rows): no key loads, no tests, IADD3 takes both points of a pack
+            int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int i2 = 4 * it + slot;
-            const float2 tw = __fmul2_rn(__fmul2_rn(wxp[i2], wyp[i2]), wzp[i2]);
-            const float2 cx = __fmul2_rn(sc2, __fmul2_rn(tw, vxp[i2]));
-            const float2 cy = __fmul2_rn(sc2, __fmul2_rn(tw, vyp[i2]));
-            const float2 cz = __fmul2_rn(sc2, __fmul2_rn(tw, vzp[i2]));
-            const float2 cd = __fmul2_rn(sc2, tw);
-            const int2 k = kp[i2];
-            // key -1 points may carry garbage weights: they match neither K0 nor K1 (both != -1 when used)
-            const int ix0 = __float2int_rz(cx.x), iy0 = __float2int_rz(cy.x), iz0 = __float2int_rz(cz.x);
-            const int ix1 = __float2int_rz(cx.y), iy1 = __float2int_rz(cy.y), iz1 = __float2int_rz(cz.y);
-            int id0, id1;
-            if (MAGIC) {
-                id0 = __float_as_int(__fadd_rz(cd.x, 8388608.0f)) - 0x4B000000; id1 = __float_as_int(__fadd_rz(cd.y, 8388608.0f)) - 0x4B000000;
-            } else { id0 = __float2int_rz(cd.x); id1 = __float2int_rz(cd.y); }
-            if (k.x == K0) { a0 += ix0; a1 += iy0; a2 += iz0; a3 += id0; }
-            if (k.y == K0) { a0 += ix1; a1 += iy1; a2 += iz1; a3 += id1; }
-            if (K1 != -1) {
-                if (k.x == K1) { e0 += ix0; e1 += iy0; e2 += iz0; e3 += id0; }
-                if (k.y == K1) { e0 += ix1; e1 += iy1; e2 += iz1; e3 += id1; }
+            for (int it = 0; it < 2; ++it) {
+                const float4 WX = wxp[4 * it], WY = wyp[4 * it], WZ = wzp[4 * it], VX = vxp[4 * it], VY = vyp[4 * it], VZ = vzp[4 * it];
+                int2 ix, iy, iz, id;
+                splat_pack_ints<MAGIC>(sc2, make_float2(WX.x, WX.y), make_float2(WY.x, WY.y), make_float2(WZ.x, WZ.y), make_float2(VX.x, VX.y), make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y), ix, iy, iz, id);
+                a0 += ix.x + ix.y; a1 += iy.x + iy.y; a2 += iz.x + iz.y; a3 += id.x + id.y;
+                splat_pack_ints<MAGIC>(sc2, make_float2(WX.z, WX.w), make_float2(WY.z, WY.w), make_float2(WZ.z, WZ.w), make_float2(VX.z, VX.w), make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w), ix, iy, iz, id);
+                a0 += ix.x + ix.y; a1 += iy.x + iy.y; a2 += iz.x + iz.y; a3 += id.x + id.y;
             }
+            splat_flush_cell(P, grid, lane, K0, a0, a1, a2, a3);
+            continue;
         }
-        // ---- end of row: accumulators -> grid ---------------------------------------------------------
-        splat_flush_cell(P, grid, lane, K0, a0, a1, a2, a3);
-        if (K1 != -1) splat_flush_cell(P, grid, lane, K1, e0, e1, e2, e3);
-        }
-    }
-}
-
-// ---- K_splat, REDUX variant ---------------------------------------------------------------------------
-// lane = strand throughout: each lane turns its point into the 32 integers, every distinct base cell of the
-// row is summed across the warp with 32 REDUX.SUM (members masked in), each lane picks the sum of its own
-// (corner, component) with a 5-level select tree and one warp-wide RED.64 goes to the grid.
-__device__ __forceinline__ int pick_by_lane(const int (&s)[32], int lane) {
-    int t16[16], t8[8], t4[4], t2[2];
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) t16[i] = b4 ? s[i + 16] : s[i];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t8[i] = b3 ? t16[i + 8] : t16[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) t4[i] = b2 ? t8[i + 4] : t8[i];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) t2[i] = b1 ? t4[i + 2] : t4[i];
-    return b0 ? t2[1] : t2[0];
-}
-
-__global__ void __launch_bounds__(kSplatThreads)
-k_grid_splat_redux(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid) {
-    constexpr unsigned kFull = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * kSplatThreads + threadIdx.x;
-    const bool live = s < P.S;
-    if (!__any_sync(kFull, live)) return;
-    const int comp = lane & 3, ca = (lane >> 2) & 1, cb = (lane >> 3) & 1, cc = (lane >> 4) & 1;   // j = comp + 4*(a + 2b + 4c)
-    const size_t RS = (size_t)P.S_pad * 6;
-    const float* nextp = planes + tiled_index(6, P.S_pad, 1, 0, s);
-    float nx[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
-    for (int r = 1; r < P.N; ++r) {
-        float c[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) c[k] = nx[k];
-        nextp += RS;
-        if (r + 1 < P.N) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
-        }
-        const AxisCells<float> X = axis_cells<float, true>(P, c[0], 0), Y = axis_cells<float, true>(P, c[1], 1), Z = axis_cells<float, true>(P, c[2], 2);
-        // some corner is a cell  <=>  -1 <= f <= G-1 on every axis
-        const bool touches = live && cell_ok(X.f[0] + 1, P.G + 1) && cell_ok(Y.f[0] + 1, P.G + 1) && cell_ok(Z.f[0] + 1, P.G + 1) && !nan3(c[0], c[1], c[2]);
-        const float vinf = fmaxf(fabsf(c[3]), fmaxf(fabsf(c[4]), fabsf(c[5])));
-        int key = (touches && vinf <= kSplatAggVmax) ? splat_key(X.f[0], Y.f[0], Z.f[0]) : -1;
-        if (touches && key == -1) {
-            const float wx[2] = { X.w0, X.w1 }, wy[2] = { Y.w0, Y.w1 }, wz[2] = { Z.w0, Z.w1 };
-            splat_point_direct(P, grid, X.f[0], Y.f[0], Z.f[0], wx, wy, wz, c[3], c[4], c[5]);
-        }
-        unsigned rem = __ballot_sync(kFull, key != -1);
-        if (rem == 0u) continue;
-        int v[32];
-#pragma unroll
-        for (int cz = 0; cz < 2; ++cz)
-#pragma unroll
-            for (int b = 0; b < 2; ++b)
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const float tw = __fmul_rn(__fmul_rn(a ? X.w1 : X.w0, b ? Y.w1 : Y.w0), cz ? Z.w1 : Z.w0);
-                    const int j = 4 * (a + 2 * b + 4 * cz);
-                    v[j + 0] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, c[3])));
-                    v[j + 1] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, c[4])));
-                    v[j + 2] = __float2int_rz(__fmul_rn(P.scale, __fmul_rn(tw, c[5])));
-                    v[j + 3] = __float2int_rz(__fmul_rn(P.scale, tw));
-                }
+        // two cells of the row per pass (a row that straddles more cells takes another pass)
         while (rem) {
-            const int K = __shfl_sync(kFull, key, __ffs(rem) - 1);
-            const bool in = key == K;
-            const unsigned grp = __ballot_sync(kFull, in);
-            rem &= ~grp;
-            int sum[32];
-            if (grp == kFull) {
+            const int Ka = __shfl_sync(kFull, key, __ffs(rem) - 1);
+            rem &= ~__ballot_sync(kFull, key == Ka);
+            int Kb = -1;
+            if (rem) { Kb = __shfl_sync(kFull, key, __ffs(rem) - 1); rem &= ~__ballot_sync(kFull, key == Kb); }
+            int a0 = 0, a1 = 0, a2 = 0, a3 = 0;          // cell Ka
+            int e0 = 0, e1 = 0, e2 = 0, e3 = 0;          // cell Kb
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[j] = __reduce_add_sync(kFull, v[j]);
-            } else {
-                const int m = in ? -1 : 0;
+            for (int it = 0; it < 2; ++it) {
+                const float4 WX = wxp[4 * it], WY = wyp[4 * it], WZ = wzp[4 * it], VX = vxp[4 * it], VY = vyp[4 * it], VZ = vzp[4 * it];
+                const int4 KK = kp[4 * it];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[j] = __reduce_add_sync(kFull, v[j] & m);
+                for (int hf = 0; hf < 2; ++hf) {
+                    int2 ix, iy, iz, id;
+                    // key -1 points may carry garbage weights: they match neither Ka nor Kb (both != -1 when used)
+                    if (hf == 0) splat_pack_ints<MAGIC>(sc2, make_float2(WX.x, WX.y), make_float2(WY.x, WY.y), make_float2(WZ.x, WZ.y), make_float2(VX.x, VX.y), make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y), ix, iy, iz, id);
+                    else         splat_pack_ints<MAGIC>(sc2, make_float2(WX.z, WX.w), make_float2(WY.z, WY.w), make_float2(WZ.z, WZ.w), make_float2(VX.z, VX.w), make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w), ix, iy, iz, id);
+                    const int kx = hf ? KK.z : KK.x, ky = hf ? KK.w : KK.y;
+                    if (kx == Ka) { a0 += ix.x; a1 += iy.x; a2 += iz.x; a3 += id.x; }
+                    if (ky == Ka) { a0 += ix.y; a1 += iy.y; a2 += iz.y; a3 += id.y; }
+                    if (Kb != -1) {
+                        if (kx == Kb) { e0 += ix.x; e1 += iy.x; e2 += iz.x; e3 += id.x; }
+                        if (ky == Kb) { e0 += ix.y; e1 += iy.y; e2 += iz.y; e3 += id.y; }
+                    }
+                }
             }
-            const int mine = pick_by_lane(sum, lane);
-            const int fx = (K & 2047) - 2 + ca, fy = ((K >> 11) & 2047) - 2 + cb, fz = (K >> 22) - 2 + cc;
-            if (cell_ok(fx, P.G) && cell_ok(fy, P.G) && cell_ok(fz, P.G))
-                global_add(grid + 4 * (size_t)(fx + (fy + fz * P.G) * P.G) + comp, (long long)mine);
+            // ---- end of row: accumulators -> grid ---------------------------------------------------------
+            splat_flush_cell(P, grid, lane, Ka, a0, a1, a2, a3);
+            if (Kb != -1) splat_flush_cell(P, grid, lane, Kb, e0, e1, e2, e3);
         }
-    }
-}
-
-// Rows are independent in the splat (unlike the FTL chain), so blockIdx.y splits them into chunks of `rows_per_chunk`:
-// scenes with few strands (C3: 100K x 64) still fill the machine.  [P.strand0, P.strand0 + 256*gridDim.x) is the strand range of
-// this launch (the chunk-pipelined step launches one splat per strand chunk).
-#ifndef RVH_S2_MINBLOCKS
-#define RVH_S2_MINBLOCKS 6
-#endif
-template <bool MAGIC>
-__global__ void __launch_bounds__(kS2Threads, RVH_S2_MINBLOCKS)
-k_grid_splat2(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid, int rows_per_chunk) {
-    __shared__ Splat2Stage stage[kS2Threads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s0 = P.strand0 + (blockIdx.x * kS2Threads + threadIdx.x) * 2;  // S_pad is a multiple of 256: always in bounds
-    const bool live0 = s0 < P.S, live1 = s0 + 1 < P.S;
-    if (!__any_sync(0xffffffffu, live0)) return;
-    const int r0 = 1 + blockIdx.y * rows_per_chunk, r1 = min(P.N, r0 + rows_per_chunk);
-    if (r0 >= r1) return;
-    const size_t RS = (size_t)P.S_pad * 6;
-    const float* nextp = planes + tiled_index(6, P.S_pad, r0, 0, s0);
-    float2 nx[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) nx[k] = __ldg(reinterpret_cast<const float2*>(nextp + k * kTileStrands));
-    for (int r = r0; r < r1; ++r) {
-        float2 c[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) c[k] = nx[k];
-        nextp += RS;
-        if (r + 1 < r1) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) nx[k] = __ldg(reinterpret_cast<const float2*>(nextp + k * kTileStrands));
-        }
-        splat2_row<MAGIC>(P, grid, stage[warp], lane, live0, live1, c[0], c[1], c[2], c[3], c[4], c[5]);
     }
 }
 
