@@ -83,7 +83,7 @@ typedef struct {              /* every field defaults to the reference constant 
     float grid_scale;         /* 1e6f                       compute.comp:11         */
     float friction;           /* 0.08f                      compute.comp:296        */
     int   flags;              /* RVH_* bits; default RVH_GRID_ON                    */
-    int   strands_per_thread; /* 0 = auto; 1, 2 or 4 (tuning, results identical)    */
+    int   strands_per_thread; /* 0 = auto; 1 or 2 (tuning, results identical; 4 = 2) */
     float repulsion;          /* 0.2f (velocity units); RVH_REPULSION_ON only (extension)       */
 } rvh_config;
 
@@ -196,6 +196,12 @@ int rvh_draw_indirect(rvh_ctx* ctx, uint32_t out[4]);   /* {S,1,0,0}, compute.co
  * 1 = integrate+FTL+corrected velocity (+ splat and all-reduce when the grid is on),
  * 2 = grid finalize + gather. */
 int rvh_step_phases(rvh_ctx* ctx, float dt, float total_time, int phases);
+
+/* Test hook: the collider decisions (compute.comp:162 sphere, :66 ellipsoids; with RVH_SDF_ON bit 1 = head volume) this path
+ * takes for the positions it currently holds, one byte per point, [S][N] in the caller's strand order, bit 0 = sphere, bit j =
+ * collider j.  The penalty force is continuous across a collider surface, but the division by the number of colliders hit
+ * (compute.comp:182-184) is not, so tests count how often a decision differs from the oracle's (tests/test_parity_full_gpu.py). */
+int rvh_debug_hit_masks(rvh_ctx* ctx, unsigned char* out, size_t bytes);
 
 /* Per-kernel CUDA-event timing (for the roofline figure).  When enabled every step
  * brackets its kernels with events; rvh_profile_read returns accumulated milliseconds

@@ -409,6 +409,39 @@ static void integrate_strand(const orc_params* p, const float* col, float dt, fl
     }
 }
 
+/* The collider decisions of integrate_strand (compute.comp:162, :66; SDF mode: d < 0) for every point of every strand, without
+ * stepping: out[s*N + i] bit 0 = sphere, bit j = collider j (SDF mode: bit 1 = head volume).  Collision tests read the OLD
+ * position of point i (compute.comp:147), so the masks depend on the input state only. */
+void orc_hit_masks(const orc_params* p, const float* col, const float* strands, unsigned char* out) {
+    const int N = p->num_points;
+    const int sdf_on = (p->flags & ORC_SDF_ON) != 0;
+    for (int s = 0; s < p->num_strands; ++s) {
+        const float* P = strands + (size_t)s * 12 * N;
+        out[(size_t)s * N] = 0;
+        for (int i = 1; i < N; ++i) {
+            v3 cur = { P[4 * i], P[4 * i + 1], P[4 * i + 2] };
+            unsigned m = 0;
+            if (sdf_on) {
+                const float pc[3] = { cur.x, cur.y, cur.z };
+                float d, g[3];
+                if (orc_sdf_sample(pc, &d, g) && d < 0.0f) m |= 2u;
+            }
+            for (int j = 0; j < (sdf_on ? (p->num_colliders > 0 ? 1 : 0) : p->num_colliders); ++j) {
+                const float* c = col + 48 * j;
+                if (j == 0) {
+                    v3 centre = { c[12], c[13], c[14] };
+                    if (distance3(cur, centre) < p->sphere_radius) m |= 1u;
+                } else {
+                    v3 q = mat_mul_vec_xyz(c + 16, cur, 1.0f);
+                    v3 zero = { 0.f, 0.f, 0.f };
+                    if (distance3(q, zero) <= 1.0f) m |= 1u << j;
+                }
+            }
+            out[(size_t)s * N + i] = (unsigned char)m;
+        }
+    }
+}
+
 typedef struct { int lo[3], hi[3]; float g[3]; } cellrange;
 
 static inline cellrange cell_range(const orc_params* p, const float* pos) {

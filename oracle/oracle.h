@@ -126,6 +126,9 @@ void orc_expand_strands(const float* strands, int S, int N, int isolines, int di
 void orc_init_strands_reference(int S, int N, const float* roots3, const float* normals3,
                                 float* strands);
 
+/* collider decisions per point (test hook, see oracle.c) */
+void orc_hit_masks(const orc_params* p, const float* colliders, const float* strands, unsigned char* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "rvh_profile_enable", "rvh_profile_read", "rvh_sync", "rvh_last_step_ms", "rvh_kernel_launches",
     "rvh_last_error", "rvh_destroy", "rvh_collider_build", "rvh_collider_translate", "rvh_wind_fbm",
     "rvh_abi_version", "rvh_set_head_sdf", "rvh_bake_head_sdf_from_colliders", "rvh_bake_head_sdf_from_mesh",
-    "rvh_download_head_sdf", "rvh_sdf_mode", "rvh_expand_strands", "rvh_expand_device_buffers", "rvh_init_from_mesh", "rvh_download_collider_mask",
+    "rvh_download_head_sdf", "rvh_sdf_mode", "rvh_debug_hit_masks", "rvh_expand_strands", "rvh_expand_device_buffers", "rvh_init_from_mesh", "rvh_download_collider_mask",
 ]
 
 
@@ -292,6 +292,12 @@ class HairSim:
 
     def sdf_mode(self):
         return {0: "off", 1: "ldg", 2: "tma"}[int(self.L.rvh_sdf_mode(self.ctx))]
+
+    def hit_masks(self):
+        """uint8 [S, N]: the collider decisions this path takes for the state it holds (rvh_debug_hit_masks)."""
+        out = np.zeros((self.S, self.N), np.uint8)
+        self._check(self.L.rvh_debug_hit_masks(self.ctx, out.ctypes.data_as(C.POINTER(C.c_ubyte)), out.nbytes), "rvh_debug_hit_masks")
+        return out
 
     def expand(self, isolines=12, divisions=42, download=True):
         """Guide -> render strands (hair.tesc/hair.tese).  Returns (pos_width, tangent_u, ms); arrays [S, isolines, divisions+1, 4]."""

@@ -273,7 +273,6 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
         prof_begin(ctx, EV_K1);
         const int fused_gather = ctx->gather_pending ? ((flags & RVH_REPULSION_ON) ? 2 : 1) : 0;
         switch (ctx->V) {
-            case 4: launch_k1_v<4>(ctx, wind, fused_gather); break;
             case 2: launch_k1_v<2>(ctx, wind, fused_gather); break;
             default: launch_k1_v<1>(ctx, wind, fused_gather); break;
         }
@@ -325,6 +324,7 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
     if (ctx->interop_aos) {
         const int tiles = (ctx->S + kTile - 1) / kTile;
         const size_t sm = (size_t)9 * ctx->N * (kTile + 1) * sizeof(float);
+        CU(cudaFuncSetAttribute(k_pack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   // per function and device, not per context: set per launch
         k_pack_aos<<<tiles, 256, sm, ctx->stream>>>((float4*)ctx->interop_aos, ctx->planes, ctx->corr, ctx->perm, ctx->S, ctx->S_pad, ctx->N);
         ctx->launches += 1;
         CU(cudaGetLastError());
@@ -388,6 +388,9 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     if (!out || !cfg) return fail(nullptr, RVH_ERR_INVALID, "null argument");
     *out = nullptr;
     if (cfg->num_strands < 1 || cfg->num_points < 2) return fail(nullptr, RVH_ERR_INVALID, "need num_strands >= 1 and num_points >= 2");
+    // the AoS <-> planes transposes stage 9 planes x N points x 33 strands of floats in shared memory (227 KB per CTA on sm_100)
+    if ((size_t)9 * cfg->num_points * (kTile + 1) * sizeof(float) > (size_t)227 * 1024)
+        return fail(nullptr, RVH_ERR_INVALID, "num_points too large: the Strand[S] pack/unpack kernels need 9*N*33*4 bytes of shared memory (N <= 195)");
     if (cfg->grid_dim < 2 || cfg->grid_dim > 1023) return fail(nullptr, RVH_ERR_INVALID, "grid_dim out of range (2..1023: the splat's cell keys hold 10 bits per axis)");
     if ((size_t)cfg->num_strands * cfg->num_points > ((size_t)1 << 31)) return fail(nullptr, RVH_ERR_INVALID, "S*N too large for one context");
     if ((cfg->flags & RVH_REPULSION_ON) && !(cfg->flags & RVH_GRID_ON)) return fail(nullptr, RVH_ERR_INVALID, "RVH_REPULSION_ON needs RVH_GRID_ON (it reads the same voxel grid)");
@@ -405,8 +408,8 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->rank = rank; c->nranks = nranks;
     if (const char* e = std::getenv("RVH_SPLAT_WARPS")) c->splat_target_warps = std::max(1, std::atoi(e));
     int V = cfg->strands_per_thread;
-    if (V != 1 && V != 2 && V != 4) V = c->S >= 65536 ? 2 : 1;     // measured on B200: 2 strands per thread is fastest at scale
-    if ((cfg->flags & (RVH_SDF_ON | RVH_REPULSION_ON)) && V == 4) V = 2;   // the extension kernels exist for 1 and 2 strands per thread
+    if (V == 4) V = 2;                                             // round 1 shipped a 4-strand kernel: it spilled (79-106 local ops) and never won; the value is still accepted
+    if (V != 1 && V != 2) V = c->S >= 65536 ? 2 : 1;               // measured on B200: 2 strands per thread is fastest at scale
     c->V = V;
     std::memset(&c->sdf_map, 0, sizeof c->sdf_map);
     ctx = c;
@@ -429,8 +432,6 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->aos_bytes = (size_t)c->S * 48 * c->N;
     CUC(cudaMalloc(&c->aos_dev, c->aos_bytes));
     CUC(cudaEventCreate(&c->ev_a)); CUC(cudaEventCreate(&c->ev_b));
-    CUC(cudaFuncSetAttribute(k_unpack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * c->N * (kTile + 1) * (int)sizeof(float)));
-    CUC(cudaFuncSetAttribute(k_pack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * c->N * (kTile + 1) * (int)sizeof(float)));
 
     StepParams& P = c->P;
     std::memset(&P, 0, sizeof P);
@@ -552,6 +553,7 @@ static int unpack_from_staging(rvh_ctx* ctx) {
     }
     const int tiles = ctx->S_pad / kTile;
     const size_t sm = (size_t)6 * ctx->N * (kTile + 1) * sizeof(float);
+    CU(cudaFuncSetAttribute(k_unpack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));     // per function and device, not per context: set per launch
     k_unpack_aos<<<tiles, 256, sm, ctx->stream>>>((const float4*)ctx->aos_dev, ctx->planes, reorder ? ctx->perm : nullptr, ctx->S, ctx->S_pad, ctx->N, ctx->P.rest);
     CU(cudaGetLastError());
     ctx->launches += reorder ? 3 : 1;
@@ -565,6 +567,7 @@ static int pack_to_staging(rvh_ctx* ctx) {
     const int tiles = (ctx->S + kTile - 1) / kTile;
     const size_t sm = (size_t)9 * ctx->N * (kTile + 1) * sizeof(float);
     const bool reorder = ctx->perm != nullptr && !(ctx->cfg.flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
+    CU(cudaFuncSetAttribute(k_pack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_pack_aos<<<tiles, 256, sm, ctx->stream>>>((float4*)ctx->aos_dev, ctx->planes, ctx->corr, reorder ? ctx->perm : nullptr, ctx->S, ctx->S_pad, ctx->N);
     CU(cudaGetLastError());
     ctx->launches += 1;
@@ -743,6 +746,25 @@ int rvh_download_head_sdf(rvh_ctx* ctx, float* sdf, size_t bytes) {
     return RVH_OK;
 }
 
+int rvh_debug_hit_masks(rvh_ctx* ctx, unsigned char* out, size_t bytes) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!ctx->uploaded || !ctx->colliders_set) return fail(ctx, RVH_ERR_STATE, "rvh_debug_hit_masks needs strands and colliders");
+    if (!out || bytes != (size_t)ctx->S * ctx->N) return fail(ctx, RVH_ERR_INVALID, "hit masks are S*N bytes");
+    if ((ctx->cfg.flags & RVH_SDF_ON) && !ctx->sdf_dev) return fail(ctx, RVH_ERR_STATE, "RVH_SDF_ON but no head SDF");
+    CU(cudaSetDevice(ctx->cfg.device));
+    unsigned char* dev = nullptr;
+    CU(cudaMalloc(&dev, bytes));
+    const bool reorder = ctx->perm != nullptr && !(ctx->cfg.flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
+    k_hit_masks<<<148 * 8, 256, 0, ctx->stream>>>(ctx->P, ctx->planes, reorder ? ctx->perm : nullptr, dev, (ctx->cfg.flags & RVH_SDF_ON) ? 1 : 0);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dev);
+    ctx->launches += 1;
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, RVH_ERR_CUDA, std::string("rvh_debug_hit_masks: ") + cudaGetErrorString(e)); }
+    return RVH_OK;
+}
+
 int rvh_sdf_mode(rvh_ctx* ctx) { return ctx ? ctx->sdf_mode : 0; }
 
 int rvh_download_collider_mask(rvh_ctx* ctx, unsigned char* out, size_t bytes, int* dim) {
@@ -847,6 +869,12 @@ int rvh_import_strands_fd(rvh_ctx* ctx, int fd, size_t bytes) {
     if (!ctx) return RVH_ERR_INVALID;
     if (bytes < ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "imported buffer smaller than Strand[S]");
     CU(cudaSetDevice(ctx->cfg.device));
+    if (ctx->interop_mem) {                                         // re-import: release the previous mapping first
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->interop_aos) cudaFree(ctx->interop_aos);
+        cudaDestroyExternalMemory(ctx->interop_mem);
+        ctx->interop_aos = nullptr; ctx->interop_mem = nullptr;
+    }
     cudaExternalMemoryHandleDesc hd; std::memset(&hd, 0, sizeof hd);
     hd.type = cudaExternalMemoryHandleTypeOpaqueFd; hd.handle.fd = fd; hd.size = bytes;
     CU(cudaImportExternalMemory(&ctx->interop_mem, &hd));

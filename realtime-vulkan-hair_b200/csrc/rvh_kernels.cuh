@@ -608,8 +608,8 @@ __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const S
 }
 
 // ---- K1: integrate + collide + FTL + corrected velocity -------------------------------------
-// One thread owns V consecutive strands and walks them root->tip together.  V = 1: scalar; V = 2, 4:
-// strands are paired into fp32x2 packs (LDG.64 / LDG.128 deliver the packs directly).  Point i's
+// One thread owns V consecutive strands and walks them root->tip together.  V = 1: scalar; V = 2:
+// the two strands form one fp32x2 pack (LDG.64 delivers it directly).  Point i's
 // velocity is final only once d_{i+1} is known (compute.comp:213-215), so the velocity store trails the
 // position by one point.
 template <int V> struct PackOf { using T = float2; static constexpr int n = V / 2; };
@@ -1091,6 +1091,36 @@ k_grid_gather(const __grid_constant__ StepParams P, float* __restrict__ planes, 
         unsigned cand;
         gather_pack<float2, REP>(P, fgrid, px, py, pz, vx, vy, vz, cand);
         *reinterpret_cast<float2*>(q + 3 * plane) = vx; *reinterpret_cast<float2*>(q + 4 * plane) = vy; *reinterpret_cast<float2*>(q + 5 * plane) = vz;
+    }
+}
+
+// ---- test hook: the collider decisions of compute.comp:158-180 as THIS path takes them ------------------------------------
+// One byte per point (external strand order, [S][N]): bit 0 = inside the sphere (:162), bit j = inside ellipsoid j (:66), or,
+// with the head SDF, bit 1 = trilinear distance < 0.  Same device functions, same operations as point_update, so the byte is
+// the decision k_ftl_step takes for the positions currently in `planes`; tests count how often it differs from the oracle's
+// (squared-distance compare, FMA contraction: a point within an ulp of a collider surface can flip).
+__global__ void __launch_bounds__(256)
+k_hit_masks(const __grid_constant__ StepParams P, const float* __restrict__ planes, const int* __restrict__ perm, unsigned char* __restrict__ out, int sdf_on) {
+    const size_t total = (size_t)P.N * P.S;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(k / P.S), s = (int)(k - (size_t)row * P.S);
+        const size_t e = perm ? (size_t)perm[s] : (size_t)s;
+        unsigned m = 0u;
+        if (row > 0) {
+            const float cx = planes[tiled_index(6, P.S_pad, row, 0, s)], cy = planes[tiled_index(6, P.S_pad, row, 1, s)], cz = planes[tiled_index(6, P.S_pad, row, 2, s)];
+            const float dx = cx - P.sphere_c[0], dy = cy - P.sphere_c[1], dz = cz - P.sphere_c[2];
+            if (P.has_sphere && vdot3(dx, dy, dz, dx, dy, dz) < P.sphere_r2) m |= 1u;
+            if (sdf_on) {
+                const SdfTile none = { nullptr, 0, 0, 0 };
+                if (sdf_inside(P.sdf, none, cx, cy, cz)) m |= 2u;
+            } else {
+                for (int j = 0; j < P.n_ell; ++j) {
+                    float qx, qy, qz;
+                    if (ellipsoid_q<float>(P.ell[j], cx, cy, cz, qx, qy, qz) <= 1.0f) m |= 2u << j;
+                }
+            }
+        }
+        out[e * P.N + row] = (unsigned char)m;
     }
 }
 

@@ -68,6 +68,7 @@ def lib():
         L.orc_sdf_bake_colliders.argtypes = [_fp, C.c_int, _ip, _fp, C.c_float, _fp]
         L.orc_sdf_bake_mesh.argtypes = [_fp, _ip, C.c_int, _ip, _fp, C.c_float, _fp]
         L.orc_expand_strands.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp]
+        L.orc_hit_masks.argtypes = [C.POINTER(OrcParams), _fp, _fp, C.POINTER(C.c_ubyte)]
         _lib = L
     return _lib
 
@@ -140,6 +141,15 @@ def phase_gather(p, strands, grid):
     g = np.ascontiguousarray(grid, np.int64)
     lib().orc_phase_gather(C.byref(p), _f(st), g.ctypes.data_as(_i64p))
     return st
+
+
+def hit_masks(p, colliders, strands):
+    """uint8 [S, N]: the oracle's collider decisions for `strands` (bit 0 sphere, bit j collider j)."""
+    st = np.ascontiguousarray(strands, np.float32)
+    col = np.ascontiguousarray(colliders, np.float32)
+    out = np.zeros((st.shape[0], st.shape[2]), np.uint8)
+    lib().orc_hit_masks(C.byref(p), _f(col), _f(st), out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return out
 
 
 def init_strands_reference(roots, normals, N):

@@ -80,7 +80,9 @@ def test_reference_application_loop_headless(golden_c1, obj_path):
         cols[0] = orc.collider_translate(cols[0], moves[f])
     assert abs(total - float(t)) < 1e-6
     assert np.array_equal(bits(out[:, 0, 0]), bits(st[:, 0, 0]))
-    assert np.abs(out[:, 0, :, :3] - st[:, 0, :, :3]).max() <= 1e-3 * 2.5
+    err = float(np.abs(out[:, 0, :, :3] - st[:, 0, :, :3]).max())
+    print("headless loop, %d free-running frames: max |dp| = %.2e L" % (frames, err / 2.5))
+    assert err <= 1e-4 * 2.5                         # the per-step bar still holds after 4 free-running frames (chaos bound ~2e-5 L at 10)
     seg = np.linalg.norm(out[:, 0, 1:, :3].astype(np.float64) - out[:, 0, :-1, :3], axis=2)
     assert np.abs(seg / (2.5 / 9.0) - 1).max() <= 1e-5
 

@@ -1,0 +1,137 @@
+"""Full-size GPU parity (VERDICT r01 "parity holes"): the kernel instantiation the benchmark times, the BASELINE.json
+configurations at their own sizes with the grid on, and a census of the collider decisions.
+
+All through the C ABI, against the CPU oracle (`orc.step(..., threads=)` = orc_step_parallel, ~1-2 s per step at these sizes).
+Tolerances are the north star's: max |position error| <= 1e-4 * strand length per step, integer grid bit-exact given the
+same inputs.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import orc
+import rvh_b200 as rvh
+from test_parity_gpu import DT, POS_TOL_REL, bits, check_state
+
+pytestmark = pytest.mark.gpu
+THREADS = min(32, os.cpu_count() or 8)
+
+
+def draped(S, N, L, oflags, steps, T0=0.0):
+    """Oracle free run from the synthetic head: hair on the head / shoulders, busy grid, wind-driven velocities."""
+    cols = rvh.scenes.bench_colliders()
+    rest = np.float32(L) / np.float32(N - 1)
+    p = orc.default_params(S, N, oflags, rest_length=rest)
+    st = rvh.scenes.synthetic_head(S, N, L, colliders=cols)
+    for k in range(steps):
+        st, _ = orc.step(p, cols, DT, np.float32(T0) + np.float32(k) * DT, st, threads=THREADS)
+    return st, cols, p, rest
+
+
+def test_two_step_protocol_runs_the_benchmark_kernel_against_the_oracle():
+    """bench.py's steady-state step is k_ftl_step<2, wind, 105, gather> -- packed pairs, wind B, collider candidate mask, the
+    previous grid's gather fused into the load -- which needs a pending gather, i.e. a SECOND step without a read-back in
+    between, and >= 4 x 148 CTAs.  Upload oracle state k-1, run two GPU steps, compare with oracle state k+1.
+
+    Tolerance: the per-step bar (1e-4 * L) times 2, the stated two-step factor: step k+1 starts from a GPU state that is within
+    the one-step error of the oracle's (measured ~4e-7 * L), and SURVEY.md section 7 measured free-running amplification of
+    ~1.5x per step."""
+    S, N, L = 655360, 16, 2.5                                  # 2,560 CTAs of 256 strands: masked kernel + fused clear are used
+    st, cols, p, rest = draped(S, N, L, orc.GRID_ON | orc.WIND_B, steps=3, T0=0.2)
+    t0 = np.float32(0.2) + np.float32(3) * DT
+    ref1, _ = orc.step(p, cols, DT, t0, st, threads=THREADS)
+    ref2, ref_grid2 = orc.step(p, cols, DT, t0 + DT, ref1, threads=THREADS)
+    cfg = rvh.default_config(S, N, flags=rvh.GRID_ON | rvh.WIND_B, rest_length=float(rest), strands_per_thread=2)
+    sim = rvh.HairSim(cfg)
+    sim.set_colliders(cols)
+    sim.upload(st)
+    assert sim.collider_mask() is not None
+    sim.step(DT, float(t0))                                    # k_ftl_step<2,1,5,0>, splat, finalize; gather left pending
+    sim.step(DT, float(t0 + DT))                               # k_ftl_step<2,1,105,1>: the benchmark's kernel
+    out = sim.download()                                       # applies the second step's gather stand-alone
+    grid = sim.download_grid()
+    sim.close()
+    Ltot = float(rest) * (N - 1)
+    perr = np.abs(out[:, 0, :, :3] - ref2[:, 0, :, :3]).max()
+    verr = np.abs(out[:, 1, :, :3] - ref2[:, 1, :, :3]).max()
+    print("two-step: pos err %.3e (%.2e L), vel err %.3e" % (perr, perr / Ltot, verr))
+    assert perr <= 2 * POS_TOL_REL * Ltot
+    assert verr <= 2 * POS_TOL_REL * Ltot / float(DT)
+    assert np.array_equal(bits(out[:, 0, 0]), bits(st[:, 0, 0]))
+    seg = np.linalg.norm(out[:, 0, 1:, :3].astype(np.float64) - out[:, 0, :-1, :3], axis=2)
+    assert np.abs(seg / float(rest) - 1).max() <= 1e-5
+    # the second step's grid: same occupied cells up to boundary flips, totals within one unit per contribution
+    assert abs(int(grid[:, 3].sum()) - int(ref_grid2[:, 3].sum())) <= 8 * S * N
+
+
+@pytest.mark.parametrize("name,S,N,L", [("C3", 100000, 64, 2.5), ("C4", 1000000, 16, 0.4)])
+def test_baseline_configs_full_size_one_step_with_grid(name, S, N, L):
+    """BASELINE.json configs[2] and configs[3] at their own sizes, grid on: one step from a settled oracle state against
+    orc_step_parallel; the integer grid bit-exact against the oracle's splat of the downloaded mid-state."""
+    st, cols, p, rest = draped(S, N, L, orc.GRID_ON, steps=2)
+    T = np.float32(2) * DT
+    ref, ref_grid = orc.step(p, cols, DT, T, st, threads=THREADS)
+    cfg = rvh.default_config(S, N, flags=rvh.GRID_ON, rest_length=float(rest))
+    sim = rvh.HairSim(cfg)
+    sim.set_colliders(cols)
+    sim.upload(st)
+    sim.step_phases(DT, float(T), 1)                           # integrate + FTL + corrected velocity + splat
+    mid = sim.download()
+    grid = sim.download_grid()
+    sim.step_phases(DT, float(T), 2)                           # finalize + gather
+    out = sim.download()
+    sim.close()
+    perr, verr = check_state(out, ref, float(rest), N, what=name)
+    print("%s full size: pos err %.3e vel err %.3e" % (name, perr, verr))
+    _, want_grid = orc.phase_splat(p, DT, mid)                 # zero correctionVecs in `mid`: a pure splat of the GPU's own mid-state
+    assert np.array_equal(grid, want_grid), "%s grid integers differ in %d cells" % (name, int(np.any(grid != want_grid, axis=1).sum()))
+    assert abs(int(grid[:, 3].sum()) - int(ref_grid[:, 3].sum())) <= 8 * S * N
+    assert grid[:, 3].max() > 2 ** 31 or name == "C3"          # C4's fur density overflows an int32 cell: int64 matters
+
+
+def test_collider_decision_census_on_a_draped_scene():
+    """rsqrt.approx / FMA contraction / squared-distance compares can flip `inside collider j` for a point within an ulp of the
+    surface.  The force is continuous there, but the division by the hit count (compute.comp:182-184) is not.  Count the
+    flips on a scene lying on head, neck, bust and shoulders: < 1e-5 of the points."""
+    S, N, L = 200000, 32, 2.5
+    st, cols, p, rest = draped(S, N, L, orc.GRID_ON, steps=40)
+    want = orc.hit_masks(p, cols, st)
+    cfg = rvh.default_config(S, N, flags=rvh.GRID_ON, rest_length=float(rest))
+    sim = rvh.HairSim(cfg)
+    sim.set_colliders(cols)
+    sim.upload(st)
+    got = sim.hit_masks()
+    sim.step(DT, 0.0)
+    out = sim.download()
+    sim.close()
+    inside = (want != 0).mean()
+    multi = (np.unpackbits(want.reshape(-1, 1), axis=1).sum(axis=1) >= 2).mean()
+    flips = int((got != want).sum())
+    print("census: %.1f%% of points inside a collider, %.2f%% inside two or more, %d decision flips of %d points" % (100 * inside, 100 * multi, flips, S * (N - 1)))
+    assert inside > 0.05, "scene must engage the colliders"
+    assert flips <= 1e-5 * S * (N - 1)
+    # (the other data-dependent branches -- the velocity clamp at |v| = vmax, compute.comp:198-200, and the sphere / ellipsoid
+    # penalty at zero depth -- are continuous across their thresholds, so a flipped decision there changes nothing beyond rounding)
+    ref, _ = orc.step(p, cols, DT, 0.0, st, threads=THREADS)
+    check_state(out, ref, float(rest), N, what="census scene")
+
+
+def test_free_running_ten_steps_stay_within_the_chaos_bound(golden_c1):
+    """Free-running comparison is only meaningful for <~10 steps (two CPU builds of the same text differ by
+    2.3e-5 * L after 10 steps, 6.4e-2 * L after 100).  From the reference's own violent initial state (Strand.cpp:157-175)."""
+    st, cols = golden_c1["state0"], golden_c1["colliders"]
+    sim = rvh.HairSim(rvh.default_config(900, 10, flags=rvh.GRID_ON | rvh.GRID_INT32_WRAP))
+    sim.set_colliders(cols)
+    sim.upload(st)
+    p = orc.default_params(900, 10, orc.GRID_ON | orc.GRID_INT32_WRAP)
+    ref = st.copy()
+    errs = []
+    for k in range(10):
+        sim.step(DT, float(k) * float(DT))
+        ref, _ = orc.step(p, cols, DT, np.float32(k) * DT, ref)
+        errs.append(float(np.abs(sim.download()[:, 0, :, :3] - ref[:, 0, :, :3]).max()) / 2.5)
+    sim.close()
+    print("free run, max |dp| / L per step:", " ".join("%.1e" % e for e in errs))
+    assert errs[0] <= POS_TOL_REL
+    assert errs[-1] <= 5e-5, "10 free-running steps drifted %.2e L (measured 1.1e-5 on B200)" % errs[-1]

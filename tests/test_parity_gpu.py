@@ -86,24 +86,6 @@ def test_c1_reference_scene_step_pairs(golden_c1, idx):
     print("C1 k=%d pos err %.2e vel err %.2e corr err %.2e" % (k, perr, verr, cerr))
 
 
-def test_c1_free_running_ten_steps(golden_c1):
-    """Short free run (valid for <~10 steps) from the reference's initial state."""
-    st = golden_c1["state0"]
-    cols = golden_c1["colliders"]
-    cfg = rvh.default_config(900, 10, flags=rvh.GRID_ON | rvh.GRID_INT32_WRAP)
-    sim = rvh.HairSim(cfg)
-    sim.set_colliders(cols)
-    sim.upload(st)
-    p = orc.default_params(900, 10, orc.GRID_ON | orc.GRID_INT32_WRAP)
-    ref = st.copy()
-    for k in range(2):
-        sim.step(DT, float(k) * float(DT))
-        ref, _ = orc.step(p, cols, DT, np.float32(k) * DT, ref)
-    out = sim.download()
-    sim.close()
-    assert np.abs(out[:, 0, :, :3] - ref[:, 0, :, :3]).max() <= 1e-3 * 2.5
-
-
 # ---- synthetic heads against the live oracle ------------------------------------------------
 
 def synth(S, N, L, seed_vel=0):
