@@ -161,10 +161,33 @@ def _ref_tag(N, flags_s):
     return tag if orc.ref_available(tag) else None
 
 
-def _ref_worker(tag, S, N, L, first, steps, warmup, barrier, q):
-    """One process = one host core = one dispatch stream of the reference shader text over its own strands."""
+_HOOK_T = C.CFUNCTYPE(None, C.c_int, C.c_void_p, C.c_size_t)
+
+
+def _ref_worker(tag, idx, cores, S, N, L, first, steps, warmup, barrier, partial_raw, total_raw, cells4, q, want_state=False):
+    """One process = one host core = one dispatch of the reference shader text over its own strand range of ONE head: at the
+    shader's third barrier (compute.comp:255, splat done / gather next) the processes sum their int32 grids through shared
+    memory, exactly what one dispatch over all strands accumulates (int32, wrapping), so the gather sees every strand."""
     import orc
     import rvh_b200 as rvh
+    lib = orc.ref_compute(tag)
+    partial = np.frombuffer(partial_raw, np.int32).reshape(cores, cells4)
+    total = np.frombuffer(total_raw, np.int32)
+    lo, hi = (cells4 * idx) // cores, (cells4 * (idx + 1)) // cores
+
+    def hook(k, grid_ptr, nbytes):
+        if k != 3:
+            return
+        g = np.ctypeslib.as_array(C.cast(grid_ptr, C.POINTER(C.c_int32)), shape=(cells4,))
+        partial[idx, :] = g
+        barrier.wait()
+        total[lo:hi] = partial[:, lo:hi].sum(axis=0, dtype=np.int32)          # int32 wrap-around = the shader's atomicAdd
+        barrier.wait()
+        g[:] = total
+
+    cb = _HOOK_T(hook)
+    if cores > 1:
+        lib.ref_set_barrier_hook(cb)
     cols = rvh.scenes.bench_colliders()
     st = rvh.scenes.synthetic_head(S, N, L, first_strand=first, colliders=cols)
     for w in range(warmup):
@@ -174,53 +197,76 @@ def _ref_worker(tag, S, N, L, first, steps, warmup, barrier, q):
     for k in range(steps):
         st, _, _ = orc.ref_dispatch(tag, st, cols, DT, DT * (warmup + k))
     el = time.perf_counter() - t0
-    q.put(el)
+    q.put((el, idx, st if want_state else None))
 
 
-def time_reference(workload, flags_s, steps, warmup, strands_per_proc=8192):
-    """Times the reference's CPU implementation of the path on a bounded sample.  Returns (value, info dict)."""
+def ref_multiprocess_run(tag, per, N, L, cores, steps, warmup, want_state=False):
+    """`cores` processes x `per` strands of one synthetic head through the reference shader text, grids shared (see _ref_worker).
+    Returns (seconds of the timed steps = max over the processes, final Strand[cores*per] or None)."""
+    import orc
+    G = orc.ref_compute(tag).ref_shader_grid_dim()
+    cells4 = G * G * G * 4
+    ctx = mp.get_context("fork")
+    partial_raw = ctx.RawArray("i", cores * cells4)
+    total_raw = ctx.RawArray("i", cells4)
+    q, bar = ctx.Queue(), ctx.Barrier(cores)
+    procs = []
+    for i in range(cores):
+        pr = ctx.Process(target=_ref_worker, args=(tag, i, cores, per, N, L, i * per, steps, warmup, bar, partial_raw, total_raw, cells4, q, want_state))
+        pr.start()
+        procs.append(pr)
+    res = sorted([q.get() for _ in procs], key=lambda r: r[1])
+    for pr in procs:
+        pr.join()
+    state = np.concatenate([r[2] for r in res]) if want_state else None
+    return max(r[0] for r in res), state
+
+
+REF_MAX_STRANDS = 1 << 20      # the reference arm's bounded sample: at most this many strands per step (the whole workload at N = 1 GPU)
+
+
+def time_reference(workload, flags_s, steps, warmup, max_strands=REF_MAX_STRANDS, S_total=None):
+    """Times the reference's CPU implementation of the path.  Returns (value, seconds, info dict)."""
     import orc
     import rvh_b200 as rvh
     S_full, N, L, _, _ = WORKLOADS[workload]
+    S_full = S_total or S_full
     cores = os.cpu_count() or 1
     tag = _ref_tag(N, flags_s) if abs(L - 2.5) < 1e-6 else None      # the shader hard-codes strand length 2.5 (compute.comp:139)
     if "sdf" in flags_s or "rep" in flags_s:
         tag = None                                                   # extensions do not exist in the shader: only the C port has them
     if workload == "c1" and tag is not None:
         # the whole workload is 900 strands: one dispatch of the reference shader text per step, one core, exactly as shipped
+        orc.ref_compute(tag)
         st, cols = c1_scene()
         for w in range(warmup):
             st, _, _ = orc.ref_dispatch(tag, st, cols, DT, DT * w)
-        reps = 20
         t0 = time.perf_counter()
-        for k in range(steps * reps):
+        for k in range(steps):
             st, _, _ = orc.ref_dispatch(tag, st, cols, DT, DT * (warmup + k))
-        el = (time.perf_counter() - t0) / reps
-        info = {"kind": "reference", "cores": 1,
-                "sample": "the full workload: 900 strands x 10 points per step, %d x %d steps: the reference's compute.comp text compiled as C++ against its vendored glm "
-                          "(oracle/_ref/libref_compute_%s.so), one dispatch per step on one core, -O2" % (steps, reps, tag)}
+        el = time.perf_counter() - t0
+        info = {"kind": "reference", "cores": 1, "strands_measured": 900,
+                "sample": "the full workload: 900 strands x 10 points per step, %d steps: the reference's compute.comp text compiled as C++ against its vendored glm "
+                          "(oracle/_ref/libref_compute_%s.so), one dispatch per step on one core, -O2" % (steps, tag)}
         return 900 * N * steps / el, el, info
     if tag is not None:
-        # the shader TU keeps its buffers in globals, so each core runs its own process over its own strand range; the
-        # grid is per process (as if the head were dispatched in `cores` independent pieces): same arithmetic per point
-        procs = []
-        ctx = mp.get_context("fork")
-        q, bar = ctx.Queue(), ctx.Barrier(cores)
-        for i in range(cores):
-            p = ctx.Process(target=_ref_worker, args=(tag, strands_per_proc, N, L, i * strands_per_proc, steps, warmup, bar, q))
-            p.start()
-            procs.append(p)
-        els = [q.get() for _ in procs]
-        for p in procs:
-            p.join()
-        el = max(els)
-        S = strands_per_proc * cores
-        info = {"kind": "reference", "cores": cores,
-                "sample": "%d strands x %d points per step (%d per core), %d steps: the reference's compute.comp text compiled as C++ against its vendored glm "
-                          "(oracle/_ref/libref_compute_%s.so), one process per host core, -O2, no Vulkan/lavapipe in this image" % (S, N, strands_per_proc, steps, tag)}
+        # the shader TU keeps its buffers in globals, so each core runs its own process over its own strand range of the same
+        # head; the int32 grids are summed across the processes before the gather (see _ref_worker): no work is skipped
+        orc.ref_compute(tag)                                         # also maps oracle/_ref into THIS process (the forked workers inherit it)
+        S = min(S_full, max_strands)
+        per = (S + cores - 1) // cores
+        S = per * cores if per * cores <= S_full else S
+        per = S // cores
+        S = per * cores
+        el, _ = ref_multiprocess_run(tag, per, N, L, cores, steps, warmup)
+        info = {"kind": "reference", "cores": cores, "strands_measured": S,
+                "sample": "%d strands x %d points per step%s, %d steps after %d warm-up: the reference's compute.comp text compiled as C++ against its vendored glm "
+                          "(oracle/_ref/libref_compute_%s.so, -O2; no Vulkan/lavapipe in this image), one process per host core over its own strand range of one head, "
+                          "the int32 grids summed across the processes at the shader's splat/gather barrier so that every strand meets every other in the grid"
+                          % (S, N, " (the whole workload)" if S == S_full else " (bounded sample of the %d-strand workload; throughput is linear in strands)" % S_full, steps, warmup, tag)}
         return S * N * steps / el, el, info
     # fall back to the OpenMP C port
-    S = min(S_full, 131072)
+    S = min(S_full, max_strands)
     cols = rvh.scenes.bench_colliders()
     st = rvh.scenes.synthetic_head(S, N, L)
     rest = np.float32(L) / np.float32(N - 1)
@@ -244,23 +290,37 @@ def time_reference(workload, flags_s, steps, warmup, strands_per_proc=8192):
     for k in range(steps):
         one(DT * (warmup + k))
     el = time.perf_counter() - t0
-    info = {"kind": "port", "cores": threads,
+    info = {"kind": "port", "cores": threads, "strands_measured": S,
             "sample": "%d strands x %d points per step, %d steps: C restatement of compute.comp (oracle/oracle.c, OpenMP over strands); "
                       "oracle/_ref has no build of this variant (strand length %.2f / N=%d%s)" % (S, N, steps, L, N, "; extension flags" if ("sdf" in flags_s or "rep" in flags_s) else "")}
     return S * N * steps / el, el, info
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line: the workload only, identical for both arms (--impl b200 / reference)."""
+    S, N, L, flags_s, desc = WORKLOADS[args.workload]
+    if args.flags is not None:
+        flags_s = args.flags
+        desc += " [flags overridden: %s]" % flags_s
+    S_total = S * world if args.scaling == "weak" else S
+    state_mb = (S_total // world if args.scaling == "strong" else S) * N * 24 / 1e6
+    return {"workload": args.workload, "description": desc, "features": flags_s, "strands_per_gpu": S if args.scaling == "weak" else S_total // world,
+            "strands_total": S_total, "points_per_strand": N, "strand_length": L, "dt": DT, "scaling": args.scaling,
+            "l2": "state %.0f MB per GPU > 126 MB L2, no flush needed" % state_mb if state_mb > 126 else "state %.1f MB is L2-resident (launch/latency-bound config)" % state_mb}
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
-        return 0
-    S_full, N, L, flags_s, desc = WORKLOADS[args.workload]
-    steps = max(1, min(args.steps, 5))                     # each step is a bounded sample; keep the whole run to a few minutes
-    warmup = max(1, min(args.warmup, 2))
-    val, el, info = time_reference(args.workload, flags_s, steps, warmup)
+        return 0                                           # rank 0 alone runs the CPU arm
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cfg = workload_config(args, world)
+    steps = max(1, min(args.steps, 40))                    # 1M x 32 takes ~1.4 s per step on 16 cores: the default --steps 300 is capped, the line says what ran
+    warmup = max(1, min(args.warmup, 10))
+    val, el, info = time_reference(args.workload, cfg["features"], steps, warmup, S_total=cfg["strands_total"])
     out = {"impl": "reference", "metric": "strand-point updates/sec", "value": val, "unit": UNIT,
            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * el / steps,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": args.workload, "description": desc, "strands_per_gpu": S_full, "points_per_strand": N, "dt": DT},
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": cfg,
            "cpu_baseline": dict(info, value=val, unit=UNIT),
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}

@@ -107,7 +107,7 @@ def run(cmd, out=None, deps=()):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
-    ap.add_argument("--points", type=int, nargs="*", default=[10, 16, 32])
+    ap.add_argument("--points", type=int, nargs="*", default=[10, 16, 32, 64])
     ap.add_argument("--wind", nargs="*", default=["", "B", "A"])
     args = ap.parse_args()
     ref = args.reference

@@ -13,6 +13,10 @@
  *     barrier is GLOBAL across workgroups (the "intended" semantics);
  *   - atomicAdd is a plain add (fibers are cooperative, one OS thread);
  *   - vkCmdFillBuffer(grid, 0) before the dispatch (Renderer.cpp:2063).
+ *   - an optional barrier hook (ref_set_barrier_hook) is called once every invocation has reached barrier k (k = 1, 2, 3
+ *     in compute.comp order: :130, :208, :255) with the grid buffer, so that several PROCESSES -- one per host core, each
+ *     dispatching its own strand range of one head -- can sum their grids before the gather: bench.py --impl reference;
+ *   - fiber stacks live in a grow-only arena, so a steady-state dispatch pays no page faults for them.
  * Invocations: exactly S by default.  The shader has no `idx < S` guard and the
  * reference dispatches 32*ceil((S+31)/32) (Renderer.cpp:2070); emulate_oob=1 runs those
  * extra invocations on a zero-filled tail, which is one possible outcome of that
@@ -40,6 +44,10 @@ static ucontext_t g_sched;
 static ucontext_t* g_current = nullptr;
 static bool g_done_flag = false;
 
+static void (*g_barrier_hook)(int, void*, size_t) = nullptr;
+static char* g_arena = nullptr;
+static size_t g_arena_bytes = 0;
+
 static void barrier() { swapcontext(g_current, &g_sched); }
 
 static void fiber_entry() {
@@ -52,6 +60,7 @@ extern "C" {
 
 int ref_shader_num_curve_points(void) { return NUM_CURVE_POINTS; }
 int ref_shader_grid_dim(void) { return GRID_DIM; }
+void ref_set_barrier_hook(void (*fn)(int, void*, size_t)) { g_barrier_hook = fn; }
 
 /* strands: Strand[S] (in/out); colliders: Collider[NUM_COLLIDERS]; grid_out: GridCell[GRID_DIM^3]
  * (int32 x4) after the dispatch; indirect_out: {vertexCount, instanceCount, firstVertex, firstInstance}. */
@@ -70,8 +79,13 @@ int ref_compute_dispatch(int S, float* strands, const float* colliders48, float 
 
     const size_t stack_bytes = 32 * 1024 + 8 * sizeof(Strand);
     std::vector<ucontext_t> ctx((size_t)inv);
-    char* stacks = (char*)std::malloc(stack_bytes * (size_t)inv);
-    if (!stacks) return -1;
+    if (g_arena_bytes < stack_bytes * (size_t)inv) {
+        std::free(g_arena);
+        g_arena_bytes = stack_bytes * (size_t)inv;
+        g_arena = (char*)std::malloc(g_arena_bytes);
+        if (!g_arena) { g_arena_bytes = 0; return -1; }
+    }
+    char* stacks = g_arena;
     std::vector<char> done((size_t)inv, 0);
     for (int i = 0; i < inv; ++i) {
         getcontext(&ctx[i]);
@@ -80,7 +94,7 @@ int ref_compute_dispatch(int S, float* strands, const float* colliders48, float 
         ctx[i].uc_link = &g_sched;
         makecontext(&ctx[i], fiber_entry, 0);
     }
-    int remaining = inv;
+    int remaining = inv, pass = 0;
     while (remaining > 0) {
         for (int i = 0; i < inv; ++i) {
             if (done[i]) continue;
@@ -90,8 +104,9 @@ int ref_compute_dispatch(int S, float* strands, const float* colliders48, float 
             swapcontext(&g_sched, &ctx[i]);
             if (g_done_flag) { done[i] = 1; --remaining; }
         }
+        ++pass;                                               /* every live invocation now waits at barrier number `pass` */
+        if (remaining > 0 && g_barrier_hook) g_barrier_hook(pass, (void*)&grid, sizeof(grid));
     }
-    std::free(stacks);
     std::memcpy(strands, buf.data(), sizeof(Strand) * (size_t)S);
     if (grid_out) std::memcpy(grid_out, &grid, sizeof(grid));
     if (indirect_out) std::memcpy(indirect_out, &numStrands, 16);

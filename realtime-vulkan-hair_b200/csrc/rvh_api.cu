@@ -61,10 +61,11 @@ struct rvh_ctx {
     float* corr = nullptr;                // [3][N][S_pad] (RVH_KEEP_CORRECTION)
     unsigned long long* grid = nullptr;   // [G^3][4] int64 accumulators
     float4* fgrid = nullptr;              // [G^3] float cells for the gather (k_grid_finalize)
-    int k1_blocks = 0;
+    int k1_blocks = 0, k1_launch_blocks = 0;   // CTAs of k_ftl_step for all strands / of the launch being issued (chunked launches)
     uint4* k1_clear = nullptr; unsigned k1_clear_n = 0;    // grid clear fused into k_ftl_step (set per step)
     size_t grid_bytes = 0;
     int* perm = nullptr;                  // internal -> external strand index (Morton order)
+    bool perm_active = false;             // the planes currently hold the strands in `perm` order (false: external order)
     void* aos_dev = nullptr;              // Strand[S] staging / interop target
     size_t aos_bytes = 0;
     void* interop_aos = nullptr;          // imported VkBuffer memory (rvh_import_strands_fd)
@@ -74,6 +75,11 @@ struct rvh_ctx {
     StepParams P;
     bool uploaded = false, colliders_set = false;
     int splat_target_warps = 32768;       // RVH_SPLAT_WARPS env (tuning): the splat splits rows over blockIdx.y until it has this many warps
+    // rvh_step_n fast paths for small scenes: several steps per launch (grid off), CUDA-graph replay of the step (grid on, wind off)
+    cudaGraphExec_t step_graph = nullptr; float step_graph_dt = 0.f; unsigned step_graph_version = 0, state_version = 1; int step_graph_launches = 0;
+    // rvh_step_host pipeline: copy streams + per-chunk events
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> pipe_ev;
     bool gather_pending = false;          // fgrid holds a finalized grid whose gather has not been applied to the velocities yet
     // head SDF (extension)
     float* sdf_dev = nullptr;             // [nz][ny][nxp] node values
@@ -191,9 +197,9 @@ template <int V, bool WIND, int NELL>
 void launch_k1(rvh_ctx* c, int gather) {
     // gather: 0 = none pending, 1 = friction, 2 = friction + repulsion (extension: V <= 2 only, see create_impl)
     if (gather == 2) {
-        if constexpr (V <= 2) k_ftl_step<V, WIND, NELL, 2><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
-    } else if (gather == 1) k_ftl_step<V, WIND, NELL, 1><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
-    else if constexpr (NELL < 100) k_ftl_step<V, WIND, NELL, 0><<<c->k1_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
+        if constexpr (V <= 2) k_ftl_step<V, WIND, NELL, 2><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
+    } else if (gather == 1) k_ftl_step<V, WIND, NELL, 1><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
+    else if constexpr (NELL < 100) k_ftl_step<V, WIND, NELL, 0><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
 }
 template <int V>
 void launch_k1_v(rvh_ctx* c, bool wind, int gather) {
@@ -213,6 +219,30 @@ void launch_k1_v(rvh_ctx* c, bool wind, int gather) {
     }
     if (wind) { if (five) launch_k1<V, true, 5>(c, gather); else launch_k1<V, true, -1>(c, gather); }
     else      { if (five) launch_k1<V, false, 5>(c, gather); else launch_k1<V, false, -1>(c, gather); }
+}
+
+// k_ftl_step over the CTAs [cta0, cta0 + nctas) (a CTA covers kBlock * V strands)
+void launch_ftl(rvh_ctx* ctx, bool wind, int fused_gather, int cta0, int nctas) {
+    ctx->P.cta0 = cta0; ctx->k1_launch_blocks = nctas;
+    if (ctx->V == 2) launch_k1_v<2>(ctx, wind, fused_gather); else launch_k1_v<1>(ctx, wind, fused_gather);
+    ctx->P.cta0 = 0;
+    ctx->launches += 1;
+}
+
+// k_grid_splat over the strands [strand0, strand0 + nstrands) (multiples of 128)
+void launch_splat(rvh_ctx* ctx, int strand0, int nstrands) {
+    // enough warps to fill 148 SMs several times over: split the rows when there are few strands
+    const int warps = nstrands / 32, rows = ctx->N - 1;
+    int chunks = std::max(1, std::min(rows, (ctx->splat_target_warps + warps - 1) / warps));
+    const int rpc = (rows + chunks - 1) / chunks;
+    chunks = (rows + rpc - 1) / rpc;
+    ctx->P.strand0 = strand0;
+    if (ctx->P.scale > 0.f && ctx->P.scale < 8388608.0f)
+        k_grid_splat<true><<<dim3(nstrands / kSplatThreads, chunks), kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid, rpc);
+    else
+        k_grid_splat<false><<<dim3(nstrands / kSplatThreads, chunks), kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid, rpc);
+    ctx->P.strand0 = 0;
+    ctx->launches += 1;
 }
 
 int launch_gather(rvh_ctx* ctx) {
@@ -241,6 +271,40 @@ int allreduce_grid(rvh_ctx* ctx) {
     return RVH_OK;
 }
 
+// the time-only wind scalars of one step (compute.comp:151-152): evaluated on the host, once per step
+void wind_scalars(int wind_mode, float total_time, float& s2T, float& T3, float& amp) {
+    s2T = 2.0f * std::sin(total_time * 2.0f);
+    T3 = (float)std::fmod((double)(total_time * 3.0f), 6.283185307179586);   // sin(5z + 3T): keep the argument bounded
+    amp = (wind_mode == 2) ? 7.0f * wind_fbm(total_time) : 10.0f;
+}
+
+// Grid off: `n` steps (<= 32) in ONE launch of k_ftl_step<..., MULTI> (strands are independent; see the kernel).
+int launch_multi_step(rvh_ctx* ctx, int n, float dt, float& t) {      // t advances by n float additions of dt, exactly as n calls of rvh_step_n(1) would
+    StepParams& P = ctx->P;
+    const int flags = ctx->cfg.flags;
+    const bool wind = flags & (RVH_WIND_A | RVH_WIND_B);
+    P.dt = dt; P.inv_dt = 1.0f / dt; P.dt2 = dt * dt; P.vel_scale = P.damping / dt;
+    P.wind_mode = (flags & RVH_WIND_B) ? 2 : ((flags & RVH_WIND_A) ? 1 : 0);
+    P.multi_steps = n;
+    for (int k = 0; k < n; ++k, t += dt) {
+        float s2T = 0.f, T3 = 0.f, amp = 0.f;
+        if (wind) wind_scalars(P.wind_mode, t, s2T, T3, amp);
+        P.wind_tab[3 * k] = amp * s2T; P.wind_tab[3 * k + 1] = T3; P.wind_tab[3 * k + 2] = amp;
+    }
+    P.cta0 = 0;
+    if (ctx->V == 2) {
+        if (wind) k_ftl_step<2, true, -1, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u);
+        else      k_ftl_step<2, false, -1, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u);
+    } else {
+        if (wind) k_ftl_step<1, true, -1, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u);
+        else      k_ftl_step<1, false, -1, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u);
+    }
+    P.multi_steps = 1;
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return RVH_OK;
+}
+
 // phases: bit 0 = integrate + FTL (+ splat, all-reduce), bit 1 = grid finalize + gather.
 // lazy: leave the gather to the next step's k_ftl_step (steady-state stepping); otherwise run it now.
 int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
@@ -252,11 +316,7 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
     const int flags = ctx->cfg.flags;
     const bool grid = flags & RVH_GRID_ON, wind = flags & (RVH_WIND_A | RVH_WIND_B);
     P.wind_mode = (flags & RVH_WIND_B) ? 2 : ((flags & RVH_WIND_A) ? 1 : 0);
-    if (wind) {
-        P.wind_s2T = 2.0f * std::sin(total_time * 2.0f);
-        P.wind_T3 = (float)std::fmod((double)(total_time * 3.0f), 6.283185307179586);   // sin(5z + 3T): keep the argument bounded
-        P.wind_amp = (P.wind_mode == 2) ? 7.0f * wind_fbm(total_time) : 10.0f;
-    }
+    if (wind) wind_scalars(P.wind_mode, total_time, P.wind_s2T, P.wind_T3, P.wind_amp);
     if ((flags & RVH_SDF_ON) && !ctx->sdf_dev)
         return fail(ctx, RVH_ERR_STATE, "RVH_SDF_ON but no head SDF: call rvh_set_head_sdf or rvh_bake_head_sdf_* first");
     if (phases & 1) {
@@ -272,29 +332,14 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
         }
         prof_begin(ctx, EV_K1);
         const int fused_gather = ctx->gather_pending ? ((flags & RVH_REPULSION_ON) ? 2 : 1) : 0;
-        switch (ctx->V) {
-            case 2: launch_k1_v<2>(ctx, wind, fused_gather); break;
-            default: launch_k1_v<1>(ctx, wind, fused_gather); break;
-        }
+        launch_ftl(ctx, wind, fused_gather, 0, ctx->k1_blocks);
         prof_end(ctx);
         ctx->gather_pending = false;
-        ctx->launches += 1;
         CU(cudaGetLastError());
         if (grid) {
             prof_begin(ctx, EV_SPLAT);
-            {
-                // enough warps to fill 148 SMs several times over: split the rows when there are few strands
-                const int warps = ctx->S_pad / 32, rows = ctx->N - 1;
-                int chunks = std::max(1, std::min(rows, (ctx->splat_target_warps + warps - 1) / warps));
-                const int rpc = (rows + chunks - 1) / chunks;
-                chunks = (rows + rpc - 1) / rpc;
-                if (ctx->P.scale > 0.f && ctx->P.scale < 8388608.0f)
-                    k_grid_splat<true><<<dim3(ctx->S_pad / kSplatThreads, chunks), kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid, rpc);
-                else
-                    k_grid_splat<false><<<dim3(ctx->S_pad / kSplatThreads, chunks), kSplatThreads, 0, ctx->stream>>>(ctx->P, ctx->planes, ctx->grid, rpc);
-            }
+            launch_splat(ctx, 0, ctx->S_pad);
             prof_end(ctx);
-            ctx->launches += 1;
             CU(cudaGetLastError());
         }
         if (grid && ctx->nranks > 1) {
@@ -325,7 +370,7 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
         const int tiles = (ctx->S + kTile - 1) / kTile;
         const size_t sm = (size_t)9 * ctx->N * (kTile + 1) * sizeof(float);
         CU(cudaFuncSetAttribute(k_pack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   // per function and device, not per context: set per launch
-        k_pack_aos<<<tiles, 256, sm, ctx->stream>>>((float4*)ctx->interop_aos, ctx->planes, ctx->corr, ctx->perm, ctx->S, ctx->S_pad, ctx->N);
+        k_pack_aos<<<tiles, 256, sm, ctx->stream>>>((float4*)ctx->interop_aos, ctx->planes, ctx->corr, ctx->perm_active ? ctx->perm : nullptr, ctx->S, ctx->S_pad, ctx->N, 0, 7);
         ctx->launches += 1;
         CU(cudaGetLastError());
     }
@@ -533,6 +578,7 @@ int rvh_set_colliders(rvh_ctx* ctx, const void* colliders, int n) {
             for (int k = 0; k < 3; ++k) E.nt[r * 3 + k] = IT[k * 4 + r];
     }
     ctx->colliders_set = true;
+    ctx->state_version += 1;                                       // a captured step holds the old colliders in its kernel parameters
     return update_collider_mask(ctx, c, n);
 }
 
@@ -554,10 +600,12 @@ static int unpack_from_staging(rvh_ctx* ctx) {
     const int tiles = ctx->S_pad / kTile;
     const size_t sm = (size_t)6 * ctx->N * (kTile + 1) * sizeof(float);
     CU(cudaFuncSetAttribute(k_unpack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));     // per function and device, not per context: set per launch
-    k_unpack_aos<<<tiles, 256, sm, ctx->stream>>>((const float4*)ctx->aos_dev, ctx->planes, reorder ? ctx->perm : nullptr, ctx->S, ctx->S_pad, ctx->N, ctx->P.rest);
+    k_unpack_aos<<<tiles, 256, sm, ctx->stream>>>((const float4*)ctx->aos_dev, ctx->planes, reorder ? ctx->perm : nullptr, ctx->S, ctx->S_pad, ctx->N, ctx->P.rest, 0);
     CU(cudaGetLastError());
     ctx->launches += reorder ? 3 : 1;
     ctx->uploaded = true;
+    ctx->perm_active = reorder;
+    ctx->state_version += 1;
     ctx->gather_pending = false;          // new state: nothing of the old grid applies to it
     return RVH_OK;
 }
@@ -566,9 +614,9 @@ static int pack_to_staging(rvh_ctx* ctx) {
     { int r = flush_gather(ctx); if (r) return r; }
     const int tiles = (ctx->S + kTile - 1) / kTile;
     const size_t sm = (size_t)9 * ctx->N * (kTile + 1) * sizeof(float);
-    const bool reorder = ctx->perm != nullptr && !(ctx->cfg.flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
+    const bool reorder = ctx->perm_active;
     CU(cudaFuncSetAttribute(k_pack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_pack_aos<<<tiles, 256, sm, ctx->stream>>>((float4*)ctx->aos_dev, ctx->planes, ctx->corr, reorder ? ctx->perm : nullptr, ctx->S, ctx->S_pad, ctx->N);
+    k_pack_aos<<<tiles, 256, sm, ctx->stream>>>((float4*)ctx->aos_dev, ctx->planes, ctx->corr, reorder ? ctx->perm : nullptr, ctx->S, ctx->S_pad, ctx->N, 0, 7);
     CU(cudaGetLastError());
     ctx->launches += 1;
     return RVH_OK;
@@ -754,7 +802,7 @@ int rvh_debug_hit_masks(rvh_ctx* ctx, unsigned char* out, size_t bytes) {
     CU(cudaSetDevice(ctx->cfg.device));
     unsigned char* dev = nullptr;
     CU(cudaMalloc(&dev, bytes));
-    const bool reorder = ctx->perm != nullptr && !(ctx->cfg.flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
+    const bool reorder = ctx->perm_active;
     k_hit_masks<<<148 * 8, 256, 0, ctx->stream>>>(ctx->P, ctx->planes, reorder ? ctx->perm : nullptr, dev, (ctx->cfg.flags & RVH_SDF_ON) ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
@@ -839,7 +887,7 @@ int rvh_expand_strands(rvh_ctx* ctx, int isolines, int divisions, float* pos_wid
     }
     const size_t sm = ((size_t)3 * ctx->N * (kExpandTile + 1) + 10 * (divisions + 1) + 4 * isolines + (size_t)isolines * (divisions + 1) + kExpandTile) * sizeof(float) + (size_t)kExpandTile * isolines;
     CU(cudaFuncSetAttribute(k_expand_strands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const bool reorder = ctx->perm != nullptr && !(ctx->cfg.flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
+    const bool reorder = ctx->perm_active;
     if (ms_out) CU(cudaEventRecord(ctx->ev_a, ctx->stream));
     k_expand_strands<<<(ctx->S + kExpandTile - 1) / kExpandTile, 256, sm, ctx->stream>>>(ctx->planes, reorder ? ctx->perm : nullptr, ctx->exp_tab, ctx->exp_pw, ctx->exp_tu,
                                                                                           ctx->S, ctx->S_pad, ctx->N, isolines, divisions);
@@ -901,8 +949,50 @@ int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out) 
     if (n < 1) return fail(ctx, RVH_ERR_INVALID, "n must be >= 1");
     CU(cudaSetDevice(ctx->cfg.device));
     if (ms_out) CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+    const int flags = ctx->cfg.flags;
+    const bool grid = flags & RVH_GRID_ON, wind = flags & (RVH_WIND_A | RVH_WIND_B);
+    const bool plain = ctx->uploaded && ctx->colliders_set && dt > 0.f && ctx->profiling == 0 && !ctx->interop_aos && !(flags & RVH_SDF_ON) &&
+                       ctx->nranks == 1 && !std::getenv("RVH_NO_FAST_STEP_N");
     float t = total_time0;
-    for (int i = 0; i < n; ++i) {
+    int done = 0;
+    if (plain && !grid && n > 1) {
+        // grid off: the strands never interact, several steps ride in one launch (k_ftl_step<..., MULTI>)
+        while (done < n) {
+            const int m = std::min(32, n - done);
+            int r = launch_multi_step(ctx, m, dt, t);
+            if (r) return r;
+            done += m;
+        }
+    } else if (plain && grid && !wind && n >= 4 && (size_t)ctx->S_pad * ctx->N <= ((size_t)1 << 23)) {
+        // small scene with the grid on: the step's 3-4 launches are launch/latency-bound, replay them as one CUDA graph.  Without
+        // wind nothing in the step's kernel parameters depends on the time, so one captured step serves every later step.
+        int r = do_step(ctx, dt, t, 3, true);                       // reaches the steady state (gather pending) outside the graph
+        if (r) return r;
+        done = 1; t += dt;
+        if (!ctx->step_graph || ctx->step_graph_dt != dt || ctx->step_graph_version != ctx->state_version) {
+            if (ctx->step_graph) { cudaGraphExecDestroy(ctx->step_graph); ctx->step_graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            const long long launches0 = ctx->launches;
+            CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            r = do_step(ctx, dt, t, 3, true);
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+            const int captured = (int)(ctx->launches - launches0);
+            ctx->launches = launches0;                              // captured, not launched
+            if (r) { if (g) cudaGraphDestroy(g); return r; }
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, RVH_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); }
+            e = cudaGraphInstantiate(&ctx->step_graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { cudaGetLastError(); ctx->step_graph = nullptr; return fail(ctx, RVH_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+            ctx->step_graph_dt = dt; ctx->step_graph_version = ctx->state_version;
+            ctx->step_graph_launches = captured;
+        }
+        for (; done < n; ++done, t += dt) {
+            CU(cudaGraphLaunch(ctx->step_graph, ctx->stream));
+            ctx->launches += ctx->step_graph_launches;
+        }
+        ctx->gather_pending = true;
+    }
+    for (; done < n; ++done) {
         int r = do_step(ctx, dt, t, 3, true);
         if (r) return r;
         t += dt;
@@ -918,7 +1008,86 @@ int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out) 
     return RVH_OK;
 }
 
+// Host round trip, pipelined over strand chunks.  PCIe is the bound (2 x 32*N bytes per strand), so the copies of different
+// chunks overlap each other and the kernels: H2D(chunk c+1) runs beside unpack + k_ftl_step + splat of chunk c, and because
+// the gather only changes velocities, the POSITIONS of chunk c go back to the host right after its k_ftl_step, in the other
+// PCIe direction, while later chunks are still arriving.  Only the velocities wait for the complete grid.  The chunks are
+// taken in the caller's order (no Morton reordering: the splat is slower on unsorted strands, but it hides under the copies);
+// integer grid sums are order-independent, so the result is bit-identical to upload + step + download.
+static int step_host_pipelined(rvh_ctx* ctx, void* strands, float dt, float total_time) {
+    const int flags = ctx->cfg.flags;
+    const bool grid = flags & RVH_GRID_ON, wind = flags & (RVH_WIND_A | RVH_WIND_B);
+    StepParams& P = ctx->P;
+    P.dt = dt; P.inv_dt = 1.0f / dt; P.dt2 = dt * dt; P.vel_scale = P.damping / dt;
+    P.wind_mode = (flags & RVH_WIND_B) ? 2 : ((flags & RVH_WIND_A) ? 1 : 0);
+    if (wind) wind_scalars(P.wind_mode, total_time, P.wind_s2T, P.wind_T3, P.wind_amp);
+    const int per_cta = kBlock * ctx->V;                                  // strands per k_ftl_step CTA: 128 or 256
+    int nchunks = 16;
+    if (const char* e = std::getenv("RVH_HOST_CHUNKS")) nchunks = std::max(1, std::atoi(e));
+    const int chunk = std::max(256, ((ctx->S_pad + nchunks - 1) / nchunks + 255) / 256 * 256);
+    nchunks = (ctx->S_pad + chunk - 1) / chunk;
+    if (!ctx->h2d_stream) { CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking)); }
+    while ((int)ctx->pipe_ev.size() < 3 * nchunks + 1) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->pipe_ev.push_back(e); }
+    const size_t pitch = (size_t)48 * ctx->N, third = (size_t)16 * ctx->N;
+    char* host = (char*)strands; char* dev = (char*)ctx->aos_dev;
+    const size_t sm_un = (size_t)6 * ctx->N * (kTile + 1) * sizeof(float), sm_pk = (size_t)9 * ctx->N * (kTile + 1) * sizeof(float);
+    CU(cudaFuncSetAttribute(k_unpack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_un));
+    CU(cudaFuncSetAttribute(k_pack_aos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pk));
+    // the copy streams start after whatever the context's stream still has in flight
+    CU(cudaEventRecord(ctx->pipe_ev[3 * nchunks], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->h2d_stream, ctx->pipe_ev[3 * nchunks], 0));
+    CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->pipe_ev[3 * nchunks], 0));
+    if (grid) CU(cudaMemsetAsync(ctx->grid, 0, ctx->grid_bytes, ctx->stream));      // Renderer.cpp:2063
+    ctx->k1_clear = nullptr; ctx->k1_clear_n = 0;
+    ctx->perm_active = false; ctx->gather_pending = false; ctx->uploaded = true; ctx->state_version += 1;
+    for (int c = 0; c < nchunks; ++c) {
+        const int s0 = c * chunk, ns = std::min(chunk, ctx->S_pad - s0), ne = std::max(0, std::min(ns, ctx->S - s0));
+        cudaEvent_t ev_in = ctx->pipe_ev[3 * c], ev_pos = ctx->pipe_ev[3 * c + 1];
+        if (ne > 0) CU(cudaMemcpy2DAsync(dev + (size_t)s0 * pitch, pitch, host + (size_t)s0 * pitch, pitch, 2 * third, ne, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CU(cudaEventRecord(ev_in, ctx->h2d_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+        k_unpack_aos<<<ns / kTile, 256, sm_un, ctx->stream>>>((const float4*)ctx->aos_dev, ctx->planes, nullptr, ctx->S, ctx->S_pad, ctx->N, ctx->P.rest, s0 / kTile);
+        launch_ftl(ctx, wind, 0, s0 / per_cta, (ns + per_cta - 1) / per_cta);
+        if (grid) launch_splat(ctx, s0, ns);
+        if (ne > 0) k_pack_aos<<<(ne + kTile - 1) / kTile, 256, sm_pk, ctx->stream>>>((float4*)ctx->aos_dev, ctx->planes, ctx->corr, nullptr, ctx->S, ctx->S_pad, ctx->N, s0 / kTile, grid ? 1 : 3);
+        ctx->launches += 2;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ev_pos, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->d2h_stream, ev_pos, 0));
+        if (ne > 0) CU(cudaMemcpy2DAsync(host + (size_t)s0 * pitch, pitch, dev + (size_t)s0 * pitch, pitch, grid ? third : 2 * third, ne, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    if (grid) {
+        const int cells = P.G * P.G * P.G;
+        k_grid_finalize<<<(cells + 255) / 256, 256, 0, ctx->stream>>>((const long long*)ctx->grid, ctx->fgrid, cells, P.int32_wrap);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+        ctx->gather_pending = true;
+        { int r = launch_gather(ctx); if (r) return r; }
+        for (int c = 0; c < nchunks; ++c) {
+            const int s0 = c * chunk, ns = std::min(chunk, ctx->S_pad - s0), ne = std::max(0, std::min(ns, ctx->S - s0));
+            if (ne <= 0) break;
+            cudaEvent_t ev_vel = ctx->pipe_ev[3 * c + 2];
+            k_pack_aos<<<(ne + kTile - 1) / kTile, 256, sm_pk, ctx->stream>>>((float4*)ctx->aos_dev, ctx->planes, ctx->corr, nullptr, ctx->S, ctx->S_pad, ctx->N, s0 / kTile, 2);
+            ctx->launches += 1;
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(ev_vel, ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->d2h_stream, ev_vel, 0));
+            CU(cudaMemcpy2DAsync(host + (size_t)s0 * pitch + third, pitch, dev + (size_t)s0 * pitch + third, pitch, third, ne, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->d2h_stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RVH_OK;
+}
+
 int rvh_step_host(rvh_ctx* ctx, void* strands, size_t bytes, float dt, float total_time) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (!strands || bytes != ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "strands must be S*48*N bytes");
+    if (ctx->colliders_set && dt > 0.f && !ctx->corr && !ctx->interop_aos && ctx->nranks == 1 && ctx->S >= 131072 && !(ctx->cfg.flags & RVH_SDF_TMA) &&
+        !((ctx->cfg.flags & RVH_SDF_ON) && !ctx->sdf_dev) && !std::getenv("RVH_NO_HOST_PIPE")) {
+        CU(cudaSetDevice(ctx->cfg.device));
+        return step_host_pipelined(ctx, strands, dt, total_time);
+    }
     int r = rvh_upload_strands_aos(ctx, strands, bytes);
     if (r) return r;
     r = do_step(ctx, dt, total_time, 3, true);
@@ -1006,6 +1175,10 @@ void rvh_destroy(rvh_ctx* c) {
     cudaFree(c->sdf_dev); cudaFree(c->bake_tris); cudaFree(c->exp_tab); cudaFree(c->exp_pw); cudaFree(c->exp_tu);
     cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->fgrid); cudaFree(c->perm); cudaFree(c->aos_dev);
     cudaFree(c->sort_tmp); cudaFree(c->sort_keys); cudaFree(c->sort_keys_out); cudaFree(c->sort_ids);
+    if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+    for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);

@@ -72,6 +72,9 @@ struct StepParams {
     int cmask_dim;                          // G / 2
     SdfVolume sdf;                          // RVH_SDF_ON
     float repulsion, inv_h;                 // RVH_REPULSION_ON: v -= repulsion * h*grad(rho)/sum(D) (gather_pack); inv_h = 1/h
+    int cta0, strand0;                      // chunked launches (rvh_step_host's pipeline): first CTA of this k_ftl_step launch, first strand of this splat launch
+    int multi_steps;                        // k_ftl_step<..., MULTI>: steps per launch (grid off: strands are independent); wind_tab = per-step (amp*s2T, T3, amp)
+    float wind_tab[3 * 32];
     float splat_vagg;                       // k_grid_splat: points with |v|_inf <= splat_vagg are aggregated in int32 registers (32 contributions of <= 2^26 each)
 };
 
@@ -497,8 +500,9 @@ __device__ __forceinline__ void collision_force(const StepParams& P, const SdfTi
 // count; NELL <= -2: the head SDF replaces the ellipsoids (-2 plain loads, -3 TMA-staged tile in `tile`).
 // GATHER != 0: the previous step's gather (+ repulsion when 2) is applied to (vx,vy,vz) right before they are first used,
 // i.e. AFTER the collision tests, whose work hides the latency of the cells prefetched at the top.
+struct WindNow { float amp_s2T, T3, amp; };   // this step's time-only wind scalars (host-evaluated): wind_amp * 2 sin(2T), 3T mod 2 pi, wind_amp
 template <class T, bool WIND, int NELL, int GATHER>
-__device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const SdfTile& tile, const float4* __restrict__ fgrid,
+__device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const WindNow& W, const SdfTile& tile, const float4* __restrict__ fgrid,
                                                     T cx, T cy, T cz, T vx, T vy, T vz, T parx, T pary, T parz) {
     constexpr int n = VecTraits<T>::n;
     // NELL >= 100: NELL - 100 unrolled ellipsoids, tested only where the collider candidate mask allows (needs GATHER)
@@ -517,19 +521,19 @@ __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const S
         T cs, sn;
 #pragma unroll
         for (int i = 0; i < n; ++i) { setel(cs, i, cos_bounded(el(a1, i))); setel(sn, i, sin_bounded(el(a2, i))); }
-        fx = vfma(bc<T>(P.wind_amp * P.wind_s2T), vmul(cs, sn), fx);
+        fx = vfma(bc<T>(W.amp_s2T), vmul(cs, sn), fx);
         if (P.wind_mode == 1) {                                         // :151
             T cl;
 #pragma unroll
             for (int i = 0; i < n; ++i) setel(cl, i, fminf(fmaxf(el(cy, i) * 2.0f, 0.2f), 2.0f));
-            fz = vfma(bc<T>(-P.wind_amp), cl, fz);
+            fz = vfma(bc<T>(-W.amp), cl, fz);
         } else {                                                        // :152
-            const T a3 = vfma(cz, bc<T>(5.0f), bc<T>(P.wind_T3));
+            const T a3 = vfma(cz, bc<T>(5.0f), bc<T>(W.T3));
             T s3;
 #pragma unroll
             for (int i = 0; i < n; ++i) setel(s3, i, sin_bounded(el(a3, i)));
-            fy = vfma(bc<T>(4.0f * P.wind_amp), s3, fy);
-            fz = vfma(bc<T>(-0.6f * P.wind_amp), vadd(cy, bc<T>(3.0f)), fz);
+            fy = vfma(bc<T>(4.0f * W.amp), s3, fy);
+            fz = vfma(bc<T>(-0.6f * W.amp), vadd(cy, bc<T>(3.0f)), fz);
         }
     }
 
@@ -621,14 +625,15 @@ template <> struct PackOf<1> { using T = float; static constexpr int n = 1; };
 #ifndef RVH_K1_STREAM_LOADS
 #define RVH_K1_STREAM_LOADS 0
 #endif
-template <int V> __device__ __forceinline__ void load_packs(const float* __restrict__ p, typename PackOf<V>::T (&o)[PackOf<V>::n]) {
+// COHERENT: plain ld.global instead of the non-coherent ld.global.nc (MULTI re-reads its own stores of the previous step)
+template <int V, bool COHERENT = false> __device__ __forceinline__ void load_packs(const float* p, typename PackOf<V>::T (&o)[PackOf<V>::n]) {
 #if RVH_K1_STREAM_LOADS
     if constexpr (V == 1) { asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(o[0]) : "l"(p)); }
     else if constexpr (V == 2) { asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(o[0].x), "=f"(o[0].y) : "l"(p)); }
     else { asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0].x), "=f"(o[0].y), "=f"(o[1].x), "=f"(o[1].y) : "l"(p)); }
 #else
-    if constexpr (V == 1) { o[0] = __ldg(p); }
-    else if constexpr (V == 2) { o[0] = __ldg(reinterpret_cast<const float2*>(p)); }
+    if constexpr (V == 1) { o[0] = COHERENT ? *p : __ldg(p); }
+    else if constexpr (V == 2) { o[0] = COHERENT ? *reinterpret_cast<const float2*>(p) : __ldg(reinterpret_cast<const float2*>(p)); }
     else { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); o[0] = make_float2(t.x, t.y); o[1] = make_float2(t.z, t.w); }
 #endif
 }
@@ -695,13 +700,18 @@ __device__ __forceinline__ void sdf_stage_row(const StepParams& P, const CUtenso
     }
 }
 
-template <int V, bool WIND, int NELL, int GATHER>
+// MULTI (grid off only): P.multi_steps steps in ONE launch.  Without the grid the strands never interact, so a thread simply
+// walks its strands again (its own stores of step k are its loads of step k+1; the state of a small scene sits in L1/L2);
+// the time-only wind scalars of every step come from the host-built P.wind_tab.  A 16K x 32 scene is launch- and
+// latency-bound (3.8 us of HBM time per step): this removes the launch, rvh_step_n uses it.
+template <int V, bool WIND, int NELL, int GATHER, bool MULTI = false>
 __global__ void __launch_bounds__(kBlock, (NELL <= -2 || GATHER == 2) ? RVH_K1X_MINBLOCKS : (GATHER ? RVH_K1G_MINBLOCKS : RVH_K1_MINBLOCKS))
 k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr,
            const float4* __restrict__ fgrid, const __grid_constant__ CUtensorMap sdf_map, uint4* __restrict__ grid_clear, unsigned grid_clear_n) {
     using T = typename PackOf<V>::T;
     constexpr int NP = PackOf<V>::n;
     constexpr bool TMA = NELL == -3;
+    static_assert(!MULTI || (GATHER == 0 && !TMA), "several steps per launch need independent strands: no grid, no staged tiles");
     // The step's grid clear (Renderer.cpp:2063) rides here when the launch is wide enough: this kernel never touches the
     // int64 accumulators (it reads the float grid), the splat that fills them comes after it in the stream, and whoever
     // read them last (finalize / exchange / a download) came before it.  Saves the memset launch.
@@ -709,25 +719,28 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
         for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < grid_clear_n; k += gridDim.x * blockDim.x) grid_clear[k] = make_uint4(0u, 0u, 0u, 0u);
     __shared__ __align__(128) unsigned char sdf_raw[TMA ? sizeof(SdfStageSmem) : 16];
     SdfStageSmem& sm = *reinterpret_cast<SdfStageSmem*>(sdf_raw);
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (P.cta0 + blockIdx.x) * blockDim.x + threadIdx.x;
     const int s0 = t * V;
     if (!TMA && s0 >= P.S_pad) return;                            // TMA variant: S_pad is a multiple of kBlock*V (V <= 2), no partial CTA
     const size_t RS = (size_t)P.S_pad * 6;                      // elements per row (all tiles, six planes)
     constexpr int PK = kTileStrands;                              // plane stride inside a tile: compile-time offsets
     float* const base = planes + tiled_index(6, P.S_pad, 0, 0, s0);
 
+    const int nsteps = MULTI ? P.multi_steps : 1;
+    for (int step = 0; step < nsteps; ++step) {
+    const WindNow W = MULTI ? WindNow{ P.wind_tab[3 * step], P.wind_tab[3 * step + 1], P.wind_tab[3 * step + 2] } : WindNow{ P.wind_amp * P.wind_s2T, P.wind_T3, P.wind_amp };
     T parx[NP], pary[NP], parz[NP];
-    load_packs<V>(base, parx); load_packs<V>(base + PK, pary); load_packs<V>(base + 2 * PK, parz);
+    load_packs<V, MULTI>(base, parx); load_packs<V, MULTI>(base + PK, pary); load_packs<V, MULTI>(base + 2 * PK, parz);
     T nx[NP], ny[NP], nz[NP], nvx[NP], nvy[NP], nvz[NP];
     float* nextp = base + RS;                                     // row 1
-    load_packs<V>(nextp, nx); load_packs<V>(nextp + PK, ny); load_packs<V>(nextp + 2 * PK, nz);
-    load_packs<V>(nextp + 3 * PK, nvx); load_packs<V>(nextp + 4 * PK, nvy); load_packs<V>(nextp + 5 * PK, nvz);
+    load_packs<V, MULTI>(nextp, nx); load_packs<V, MULTI>(nextp + PK, ny); load_packs<V, MULTI>(nextp + 2 * PK, nz);
+    load_packs<V, MULTI>(nextp + 3 * PK, nvx); load_packs<V, MULTI>(nextp + 4 * PK, nvy); load_packs<V, MULTI>(nextp + 5 * PK, nvz);
     T n2x[NP], n2y[NP], n2z[NP];                                  // TMA only: positions two rows ahead
     unsigned phase = 0;                                           // TMA only: mbarrier phase bit per buffer
     int bx = 0, by = 0, bz = 0;                                   // TMA only: origin of the tile of the row being consumed
     const int wid = threadIdx.x >> 5;
     if constexpr (TMA) {
-        if (P.N > 2) { load_packs<V>(nextp + RS, n2x); load_packs<V>(nextp + RS + PK, n2y); load_packs<V>(nextp + RS + 2 * PK, n2z); }
+        if (P.N > 2) { load_packs<V, MULTI>(nextp + RS, n2x); load_packs<V, MULTI>(nextp + RS + PK, n2y); load_packs<V, MULTI>(nextp + RS + 2 * PK, n2z); }
         if ((threadIdx.x & 31) == 0) {
             mbar_init(&sm.bar[wid][0], 1); mbar_init(&sm.bar[wid][1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -751,15 +764,15 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
         SdfTile tile = { nullptr, 0, 0, 0 };
         if constexpr (!TMA) {
             if (i + 1 < P.N) {
-                load_packs<V>(nextp, nx); load_packs<V>(nextp + PK, ny); load_packs<V>(nextp + 2 * PK, nz);
-                load_packs<V>(nextp + 3 * PK, nvx); load_packs<V>(nextp + 4 * PK, nvy); load_packs<V>(nextp + 5 * PK, nvz);
+                load_packs<V, MULTI>(nextp, nx); load_packs<V, MULTI>(nextp + PK, ny); load_packs<V, MULTI>(nextp + 2 * PK, nz);
+                load_packs<V, MULTI>(nextp + 3 * PK, nvx); load_packs<V, MULTI>(nextp + 4 * PK, nvy); load_packs<V, MULTI>(nextp + 5 * PK, nvz);
             }
         } else {
             if (i + 1 < P.N) {
 #pragma unroll
                 for (int u = 0; u < NP; ++u) { nx[u] = n2x[u]; ny[u] = n2y[u]; nz[u] = n2z[u]; }
-                load_packs<V>(nextp + 3 * PK, nvx); load_packs<V>(nextp + 4 * PK, nvy); load_packs<V>(nextp + 5 * PK, nvz);
-                if (i + 2 < P.N) { load_packs<V>(nextp + RS, n2x); load_packs<V>(nextp + RS + PK, n2y); load_packs<V>(nextp + RS + 2 * PK, n2z); }
+                load_packs<V, MULTI>(nextp + 3 * PK, nvx); load_packs<V, MULTI>(nextp + 4 * PK, nvy); load_packs<V, MULTI>(nextp + 5 * PK, nvz);
+                if (i + 2 < P.N) { load_packs<V, MULTI>(nextp + RS, n2x); load_packs<V, MULTI>(nextp + RS + PK, n2y); load_packs<V, MULTI>(nextp + RS + 2 * PK, n2z); }
             }
             const int b = i & 1;
             tile.data = sm.tile[wid][b]; tile.ox = bx; tile.oy = by; tile.oz = bz;
@@ -770,7 +783,7 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
         T fvx[NP], fvy[NP], fvz[NP], odx[NP], ody[NP], odz[NP];
 #pragma unroll
         for (int u = 0; u < NP; ++u) {
-            const PointOut<T> o = point_update<T, WIND, NELL, GATHER>(P, tile, fgrid, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
+            const PointOut<T> o = point_update<T, WIND, NELL, GATHER>(P, W, tile, fgrid, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
             parx[u] = o.px; pary[u] = o.py; parz[u] = o.pz;
             odx[u] = o.dx; ody[u] = o.dy; odz[u] = o.dz;
             // finalise point i-1: v_{i-1} -= d_i / dt   (compute.comp:213-215)
@@ -787,6 +800,7 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
     }
     // last point: no correction term (compute.comp:213 `i != NUM_CURVE_POINTS - 1`)
     store_packs<V>(prevp + 3 * PK, lvx); store_packs<V>(prevp + 4 * PK, lvy); store_packs<V>(prevp + 5 * PK, lvz);
+    }   // step
 }
 
 // ---- K_splat: corrected velocities -> voxel grid (compute.comp:231-252) ----------------------------
@@ -870,7 +884,7 @@ k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ pla
     constexpr unsigned kFull = 0xffffffffu;
     __shared__ SplatStage stage[kSplatThreads / 32][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s = blockIdx.x * kSplatThreads + threadIdx.x;            // S_pad is a multiple of 128: always in bounds
+    const int s = P.strand0 + blockIdx.x * kSplatThreads + threadIdx.x;   // S_pad is a multiple of 128: always in bounds
     const bool live = s < P.S;
     if (!__any_sync(kFull, live)) return;
     const int r0 = 1 + blockIdx.y * rows_per_chunk, r1 = min(P.N, r0 + rows_per_chunk);
@@ -1131,9 +1145,9 @@ constexpr int kTile = 32;
 
 __global__ void __launch_bounds__(256)
 k_unpack_aos(const float4* __restrict__ aos, float* __restrict__ planes, const int* __restrict__ perm,
-             int S, int S_pad, int N, float rest) {
+             int S, int S_pad, int N, float rest, int first_tile) {
     extern __shared__ float sm[];            // [6][N][kTile+1]
-    const int tile0 = blockIdx.x * kTile;
+    const int tile0 = (first_tile + blockIdx.x) * kTile;
     const int q2 = 2 * N;
     for (int k = threadIdx.x; k < kTile * q2; k += blockDim.x) {
         const int sl = k / q2, q = k % q2;
@@ -1163,15 +1177,16 @@ k_unpack_aos(const float4* __restrict__ aos, float* __restrict__ planes, const i
 
 __global__ void __launch_bounds__(256)
 k_pack_aos(float4* __restrict__ aos, const float* __restrict__ planes, const float* __restrict__ corr,
-           const int* __restrict__ perm, int S, int S_pad, int N) {
+           const int* __restrict__ perm, int S, int S_pad, int N, int first_tile, int which) {
+    // which: bit 0 curvePoints, bit 1 curveVels, bit 2 correctionVecs -- only these thirds of every Strand are (read and) written
     extern __shared__ float sm[];            // [9][N][kTile+1]
-    const int tile0 = blockIdx.x * kTile;
+    const int tile0 = (first_tile + blockIdx.x) * kTile;
     const int nk = corr ? 9 : 6;
     for (int k = threadIdx.x; k < nk * N * kTile; k += blockDim.x) {
         const int sl = k % kTile, r = k / kTile;
         const int kk = r / N, j = r % N;
         float v = 0.f;
-        if (tile0 + sl < S_pad)
+        if (tile0 + sl < S_pad && ((which >> (kk / 3)) & 1))
             v = kk < 6 ? planes[tiled_index(6, S_pad, j, kk, tile0 + sl)]
                        : corr[tiled_index(3, S_pad, j, kk - 6, tile0 + sl)];
         sm[r * (kTile + 1) + sl] = v;
@@ -1183,6 +1198,7 @@ k_pack_aos(float4* __restrict__ aos, const float* __restrict__ planes, const flo
         const int s = tile0 + sl;
         if (s >= S) continue;
         const int a = q / N, j = q % N;      // a: 0 curvePoints, 1 curveVels, 2 correctionVecs
+        if (!((which >> a) & 1)) continue;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a < 2 || corr) {
             v.x = sm[((3 * a + 0) * N + j) * (kTile + 1) + sl];

@@ -43,3 +43,26 @@ def test_workload_table_names_every_baseline_config():
     assert bench.WORKLOADS["c1"][:2] == (900, 10) and bench.WORKLOADS["c5"][:2] == (4000000, 32)
     b1, b2 = bench.bytes_per_strand(32, True)
     assert b1 == 48 * 31 + 12 and b2 == 36 * 31                     # B1 and B2 - B1
+
+
+def test_reference_arm_processes_share_one_grid_bit_exactly():
+    """The reference arm splits one head over one process per core and sums the int32 grids at the shader's splat/gather
+    barrier.  Four processes x 512 strands must end, bit for bit, where ONE dispatch of the 2048 strands ends."""
+    import numpy as np
+    import pytest
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    import orc
+    import rvh_b200 as rvh
+    tag = "N10"
+    if not orc.ref_available(tag):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    per, cores, N, L, steps = 512, 4, 10, 2.5, 3
+    _, got = bench.ref_multiprocess_run(tag, per, N, L, cores, steps, 0, want_state=True)
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(per * cores, N, L, colliders=cols)
+    for k in range(steps):
+        st, _, _ = orc.ref_dispatch(tag, st, cols, bench.DT, bench.DT * k)
+    assert np.array_equal(got.view(np.uint32), st.view(np.uint32))
+    assert np.abs(got[:, 1]).max() > 0

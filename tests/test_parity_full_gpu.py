@@ -135,3 +135,83 @@ def test_free_running_ten_steps_stay_within_the_chaos_bound(golden_c1):
     print("free run, max |dp| / L per step:", " ".join("%.1e" % e for e in errs))
     assert errs[0] <= POS_TOL_REL
     assert errs[-1] <= 5e-5, "10 free-running steps drifted %.2e L (measured 1.1e-5 on B200)" % errs[-1]
+
+
+# ---- the fast paths of rvh_step_n / rvh_step_host must be invisible in the results ----------------------------------
+
+def _fresh(S, N, L, flags, st, cols, spt=0):
+    rest = float(np.float32(L) / np.float32(N - 1))
+    sim = rvh.HairSim(rvh.default_config(S, N, flags=flags, rest_length=rest, strands_per_thread=spt))
+    sim.set_colliders(cols)
+    sim.upload(st)
+    return sim
+
+
+@pytest.mark.parametrize("S,N,flags,spt", [(16384, 32, rvh.WIND_B, 0), (16384, 32, rvh.WIND_B, 2), (3000, 16, rvh.WIND_A, 1), (900, 10, 0, 0)])
+def test_step_n_without_grid_runs_many_steps_per_launch_with_the_same_result(S, N, flags, spt):
+    """Grid off: rvh_step_n puts up to 32 steps into ONE launch (k_ftl_step<..., MULTI>, per-step wind scalars from a host
+    table).  40 steps that way == 40 calls of rvh_step, bit for bit (C2's shape first)."""
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, 2.5, colliders=cols)
+    a = _fresh(S, N, 2.5, flags, st, cols, spt)
+    la = a.kernel_launches()
+    a.step_n(40, DT, 0.25)
+    assert a.kernel_launches() - la == 2                        # 32 + 8 steps
+    fa = a.download()
+    a.close()
+    # same float sequence of step times as the library (t += dt in float32): 40 free-running steps amplify a last-bit difference
+    c = _fresh(S, N, 2.5, flags, st, cols, spt)
+    t = np.float32(0.25)
+    for k in range(40):
+        c.step(DT, float(t))
+        t = np.float32(t + np.float32(DT))
+    fc = c.download()
+    c.close()
+    assert np.array_equal(bits(fa), bits(fc)), "multi-step launch differs from single steps"
+
+
+def test_step_n_replays_a_cuda_graph_on_small_grid_scenes_with_the_same_result(golden_c1):
+    """Grid on, wind off, small scene (the shipped C1 scene): rvh_step_n captures one steady-state step as a CUDA graph and
+    replays it.  Same kernels, same order: bit-identical to calling rvh_step."""
+    st, cols = golden_c1["state0"], golden_c1["colliders"]
+    flags = rvh.GRID_ON | rvh.GRID_INT32_WRAP
+    a = rvh.HairSim(rvh.default_config(900, 10, flags=flags)); a.set_colliders(cols); a.upload(st)
+    b = rvh.HairSim(rvh.default_config(900, 10, flags=flags)); b.set_colliders(cols); b.upload(st)
+    a.step_n(25, DT, 0.0)
+    a.step_n(5, DT, 25 * float(DT))                             # reuses the instantiated graph
+    for k in range(30):
+        b.step(DT, k * float(DT))
+    fa, fb, ga, gb = a.download(), b.download(), a.download_grid(), b.download_grid()
+    a.set_colliders(cols)                                       # invalidates the captured step (its kernel parameters hold the colliders)
+    a.step_n(6, DT, 0.0)
+    for k in range(6):
+        b.step(DT, 0.0)
+    fa2, fb2 = a.download(), b.download()
+    a.close(); b.close()
+    assert np.array_equal(bits(fa), bits(fb)) and np.array_equal(ga, gb)
+    assert np.array_equal(bits(fa2), bits(fb2))
+
+
+@pytest.mark.parametrize("S,N,L,flags", [(150000, 8, 0.4, rvh.GRID_ON), (140001, 12, 2.5, rvh.GRID_ON | rvh.WIND_B), (131072, 10, 2.5, rvh.WIND_B)])
+def test_pipelined_step_host_equals_upload_step_download(S, N, L, flags):
+    """Above 128K strands rvh_step_host pipelines chunked copies against the kernels and returns positions before the grid
+    is complete.  The host buffer must end bit-identical to upload + step + download (which Morton-sorts the strands)."""
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, L, colliders=cols)
+    rng = np.random.default_rng(5)
+    st[:, 1, 1:, :3] += rng.normal(scale=0.3, size=(S, N - 1, 3)).astype(np.float32)
+    ref_sim = _fresh(S, N, L, flags, st, cols)
+    ref_sim.step(DT, 0.4)
+    ref = ref_sim.download()
+    ref_sim.close()
+    sim = rvh.HairSim(rvh.default_config(S, N, flags=flags, rest_length=float(np.float32(L) / np.float32(N - 1))))
+    sim.set_colliders(cols)
+    buf = st.copy()
+    buf[:, 2] = 123.0
+    sim.step_host(buf, DT, 0.4)
+    again = sim.download()                                      # the device state after the pipelined call, through the normal path
+    sim.step(DT, 0.4 + float(DT))                               # and the context keeps stepping from it
+    sim.close()
+    assert np.array_equal(bits(buf[:, 0:2]), bits(ref[:, 0:2]))
+    assert np.all(buf[:, 2] == 123.0)
+    assert np.array_equal(bits(again[:, 0:2]), bits(ref[:, 0:2]))
