@@ -328,130 +328,179 @@ def run_reference(args):
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="ns_full", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--spt", type=int, default=0, help="strands per thread (0 auto)")
-    ap.add_argument("--flags", default=None, help="override the workload's feature flags, e.g. grid+windB (experiments)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: every rank owns the workload's strand count; strong: the count is split over the ranks")
-    ap.add_argument("--no-kernel-events", action="store_true", help="time the steps without the per-kernel CUDA events (no roofline per-kernel split)")
-    ap.add_argument("--expand", action="store_true", help="also time the guide -> render strand expansion (hair.tesc/hair.tese, 12 isolines x 42 divisions) of the final state")
-    ap.add_argument("--device-init", action="store_true", help="generate the synthetic head on the GPU (rvh_init_synthetic_head) instead of uploading it")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+class Ranks:
+    """torch.distributed plumbing (NCCL) for the N > 1 launch; every rank drives its own context."""
 
-    import torch
-    import rvh_b200 as rvh
+    def __init__(self, rvh):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        self.rvh = rvh
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    nccl_id = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.tensor(list(rvh.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().tolist())
+    def new_nccl_id(self):
+        """A fresh ncclUniqueId from rank 0 (one per sharded context)."""
+        if self.dist is None:
+            return None
+        idt = self.torch.zeros(128, dtype=self.torch.uint8, device="cuda")
+        if self.rank == 0:
+            idt = self.torch.tensor(list(self.rvh.nccl_unique_id()), dtype=self.torch.uint8, device="cuda")
+        self.dist.broadcast(idt, 0)
+        return bytes(idt.cpu().tolist())
 
-    S, N, L, flags_s, desc = WORKLOADS[args.workload]
-    S_total = S * world if args.scaling == "weak" else S
-    if args.scaling == "strong":
-        lo, hi = rvh.scenes.shard_range(S_total, rank, world)
+    def barrier(self, sim=None):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+        if sim is not None:
+            sim.sync()
+
+    def max(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_u64(self, x):
+        """Every rank's 64-bit word, on every rank."""
+        if self.dist is None:
+            return [int(x)]
+        t = self.torch.tensor([np.int64(np.uint64(x).astype(np.int64))], dtype=self.torch.int64, device="cuda")
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [int(np.uint64(np.int64(o.item()))) for o in out]
+
+
+def verification_checksum(R, rvh):
+    """A fixed scene -- 262,144 strands x 16 points, grid + wind B, 3 steps -- SHARDED over however many ranks run, reduced to
+    two 64-bit words: the wrapping sum of the reduced int64 grid and the XOR of every position/velocity bit.  The grid exchange is
+    integer and the strands are otherwise independent, so the words are the same for 1, 2, 4 and 8 GPUs: anyone can compare the
+    SCALE lines."""
+    S_total, N, L = 262144, 16, 2.5
+    lo, hi = rvh.scenes.shard_range(S_total, R.rank, R.world)
+    cols = rvh.scenes.bench_colliders()
+    cfg = rvh.default_config(hi - lo, N, flags=rvh.GRID_ON | rvh.WIND_B, device=R.local, rest_length=float(np.float32(L) / np.float32(N - 1)))
+    sim = rvh.HairSim(cfg, rank=R.rank, nranks=R.world, nccl_id=R.new_nccl_id())
+    sim.set_colliders(cols)
+    sim.init_synthetic_head(lo, L, 8)
+    for k in range(3):
+        sim.step(DT, 0.1 + k * DT)
+    grid = sim.download_grid()                                   # collective: all-reduces on demand
+    st = sim.download()
+    mode = sim.exchange_mode()
+    sim.close()
+    words = np.ascontiguousarray(st[:, 0:2]).view(np.uint64)
+    x = np.bitwise_xor.reduce(words.reshape(-1)) if words.size else np.uint64(0)
+    xs = R.gather_u64(x)
+    state_xor = 0
+    for v in xs:
+        state_xor ^= v
+    grid_sum = int(grid.astype(np.int64).view(np.uint64).sum(dtype=np.uint64))
+    return {"grid_sum_u64": "%016x" % grid_sum, "state_xor_u64": "%016x" % state_xor, "exchange": mode,
+            "what": "262144 strands x 16 points (grid + wind B), sharded over the %d rank(s), 3 steps: wrapping sum of the reduced int64 grid, XOR of all position/velocity "
+                    "words; identical for any GPU count" % R.world}
+
+
+def measure(R, rvh, args, workload, steps, warmup, scaling, full):
+    """One workload on the ranks of R: device-resident timed region (+ per-kernel split, + the end-to-end legs when `full`)."""
+    torch = R.torch
+    S, N, L, flags_s, desc = WORKLOADS[workload]
+    if full and args.flags is not None:
+        flags_s = args.flags
+    S_total = S * R.world if scaling == "weak" else S
+    if scaling == "strong":
+        lo, hi = rvh.scenes.shard_range(S_total, R.rank, R.world)
         first_strand, S = lo, hi - lo
     else:
-        first_strand = rank * S
-    device_init = args.device_init or S * N >= (1 << 26)
-    if args.flags is not None:
-        flags_s = args.flags
-        desc += " [flags overridden: %s]" % flags_s
+        first_strand = R.rank * S
+    device_init = args.device_init or S * N >= (1 << 26) or not full
     flags = parse_flags(rvh, flags_s)
     grid_on = bool(flags & rvh.GRID_ON)
     rest = float(np.float32(L) / np.float32(N - 1))
     cols = rvh.scenes.bench_colliders()
-    c1 = args.workload == "c1"
+    c1 = workload == "c1"
     if c1:
-        if world > 1 and args.scaling != "strong":
+        if R.world > 1 and scaling != "strong":
             raise SystemExit("c1 is one fixed scene of 900 strands: use --scaling strong to shard it")
         c1_state, cols = c1_scene()
         device_init = False
 
-    # synthetic inputs in pinned host memory (global strand ids => every rank makes its own shard)
     aos_bytes = S * 48 * N
-    pinned = torch.empty(aos_bytes // 4, dtype=torch.float32, pin_memory=True)
-    host = pinned.numpy().reshape(S, 3, N, 4)
-    if c1:
-        host[:] = c1_state[first_strand:first_strand + S]
-    elif not device_init:
-        rvh.scenes.synthetic_head(S, N, L, first_strand=first_strand, colliders=cols, out=host)
+    pinned = host = None
+    if full or c1:
+        # synthetic inputs in pinned host memory (global strand ids => every rank makes its own shard)
+        pinned = torch.empty(aos_bytes // 4, dtype=torch.float32, pin_memory=True)
+        host = pinned.numpy().reshape(S, 3, N, 4)
+        if c1:
+            host[:] = c1_state[first_strand:first_strand + S]
+        elif not device_init:
+            rvh.scenes.synthetic_head(S, N, L, first_strand=first_strand, colliders=cols, out=host)
 
-    cfg = rvh.default_config(S, N, flags=flags, device=local, rest_length=rest, strands_per_thread=args.spt)
-    sim = rvh.HairSim(cfg, rank=rank, nranks=world, nccl_id=nccl_id)
+    cfg = rvh.default_config(S, N, flags=flags, device=R.local, rest_length=rest, strands_per_thread=args.spt)
+    sim = rvh.HairSim(cfg, rank=R.rank, nranks=R.world, nccl_id=R.new_nccl_id())
     sim.set_colliders(cols)
     if flags & rvh.SDF_ON:
         dim, origin, cell = sdf_lattice()
         sim.bake_head_sdf_from_colliders(dim, origin, cell)     # GPU bake of the scene's own ellipsoids
     if device_init:
         sim.init_synthetic_head(first_strand, L, 8)
-        sim.download_ptr(pinned.data_ptr(), aos_bytes)                  # the e2e leg starts from the same state in host memory
+        if pinned is not None:
+            sim.download_ptr(pinned.data_ptr(), aos_bytes)              # the e2e leg starts from the same state in host memory
     else:
         sim.upload_ptr(pinned.data_ptr(), aos_bytes)
     sim.sync()
     exchange = sim.exchange_mode()
     sdf_mode = sim.sdf_mode()
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sim.sync()
+    # small scenes: rvh_step_n's fast paths (many steps per launch / CUDA-graph replay) are what a user gets; they carry no
+    # per-kernel events, so the roofline kernel's duration is the step itself there
+    S_pad = (S + 255) // 256 * 256
+    fast = None
+    if R.world == 1 and not (flags & rvh.SDF_ON):
+        if not grid_on and S * N * 24 <= 126e6:
+            fast = "up to 32 steps per launch (k_ftl_step MULTI)"
+        elif grid_on and "wind" not in flags_s and S_pad * N <= (1 << 23):
+            fast = "CUDA-graph replay of the step"
+    small = fast is not None
+    kernel_events = not (args.no_kernel_events or small)
 
     # ---- device-resident timed region -------------------------------------------------------
-    sim.step_n(max(args.warmup, 3), DT, 0.0, timed=True)
-    # CUDA events around k_ftl_step ride inside the timed region (the roofline's launch duration comes from them); what the
-    # timed region loses to them and to the clock sampler is measured right after it (`sampler_overhead_ms_per_step`)
-    sim.profile_enable(0 if args.no_kernel_events else 2)       # timed region: events around the roofline kernel only
+    sim.step_n(max(warmup, 3), DT, 0.0, timed=True)
+    sim.profile_enable(2 if kernel_events else 0)               # timed region: events around the roofline kernel only
     sim.profile_read()
     launches0 = sim.kernel_launches()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(R.local)
+    if R.rank == 0 and full:
         sampler.start()
-    barrier()
-    ms = sim.step_n(args.steps, DT, DT * args.warmup, timed=True)     # CUDA events on the context's stream
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    R.barrier(sim)
+    ms = sim.step_n(steps, DT, DT * warmup, timed=True)         # CUDA events on the context's stream
+    R.barrier(sim)
+    clocks = sampler.stop() if (R.rank == 0 and full) else None
     prof = sim.profile_read()
-    sim.profile_enable(False)
+    sim.profile_enable(0)
     launches = sim.kernel_launches() - launches0
-    n2 = min(args.steps, 50)
-    ms_plain = sim.step_n(n2, DT, DT * (args.warmup + args.steps), timed=True) / n2      # same steps with neither the clock sampler nor kernel events running
-    # the split over ALL kernels comes from a separate, untimed pass right after the timed region
+    n2 = min(steps, 50)
+    ms_plain = sim.step_n(n2, DT, DT * (warmup + steps), timed=True) / n2      # same steps with neither the clock sampler nor kernel events running
+    # the split over ALL kernels comes from a separate, untimed pass right after the timed region (one launch per kernel and step)
     k1_timed = prof["ftl_step"]
-    if not args.no_kernel_events:
-        sim.profile_enable(1)
-        sim.step_n(n2, DT, DT * (args.warmup + args.steps + n2), timed=True)
-        prof = sim.profile_read()
-        sim.profile_enable(0)
-        prof["ftl_step"] = k1_timed                                # the roofline kernel: measured inside the timed region
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = S_total * N * args.steps / (ms * 1e-3)
+    sim.profile_enable(1)
+    sim.step_n(n2, DT, DT * (warmup + steps + n2), timed=True)
+    prof = sim.profile_read()
+    sim.profile_enable(0)
+    if kernel_events:
+        prof["ftl_step"] = k1_timed                             # the roofline kernel: measured inside the timed region
+    ms = R.max(ms)
+    value = S_total * N * steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -462,14 +511,18 @@ def main():
     b1, b2 = bytes_per_strand(N, grid_on)
     per_kernel = {k: (v["ms"] / v["launches"] if v["launches"] else 0.0) for k, v in prof.items()}
     dominant = max(per_kernel, key=lambda k: per_kernel[k])
-    k1_ms = per_kernel["ftl_step"] or ms / args.steps          # --no-kernel-events: no split, the whole step stands in
+    # graph replay: the kernel is the same as in the per-kernel pass, its duration comes from there; many-steps-per-launch: the
+    # launch IS the steps, so the step time of the timed region is the per-step duration of the kernel
+    k1_ms = per_kernel["ftl_step"] if (kernel_events or (small and grid_on and per_kernel["ftl_step"])) else ms / steps
     achieved = S * b1 / (k1_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_ftl_step (integrate + collide + FTL + corrected velocity%s)" % (" + fused gather of the previous grid" if grid_on else ""),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": S * b1, "avg_launch_ms": k1_ms, "per_kernel_ms": per_kernel,
-                "per_kernel_ms_source": "ftl_step: CUDA events inside the timed region; the other kernels: events in a separate pass of %d steps right after it" % n2,
-                "longest_kernel": dominant, "sampler_overhead_ms_per_step": max(0.0, ms / args.steps - ms_plain),
-                "step_bytes": S * (b1 + b2), "step_frac": (S * (b1 + b2) / (ms / args.steps * 1e-3) / 1e9) / peak,
+                "per_kernel_ms_source": ("ftl_step: CUDA events inside the timed region; " if kernel_events else
+                                         "small scene: rvh_step_n replays the step as a CUDA graph (avg_launch_ms: k_ftl_step in the per-kernel pass) or runs many steps per launch (avg_launch_ms: step time of the timed region); ") +
+                                        "per_kernel_ms: events around every kernel in a separate pass of %d single steps right after it" % n2,
+                "longest_kernel": dominant, "sampler_overhead_ms_per_step": max(0.0, ms / steps - ms_plain),
+                "step_bytes": S * (b1 + b2), "step_frac": (S * (b1 + b2) / (ms / steps * 1e-3) / 1e9) / peak,
                 "note": "achieved = S*(48*(N-1)+12) bytes / CUDA-event time of k_ftl_step inside the timed region; step_frac = reference-shaped "
                         "step bytes S*(84*(N-1)+12) / whole step time"}
     if grid_on and per_kernel.get("grid_splat"):
@@ -482,78 +535,125 @@ def main():
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
-            roofline["traffic"] = json.load(open(traffic_path)).get(args.workload, {}).get("k_ftl_step")
+            tj = json.load(open(traffic_path))
+            roofline["traffic"] = tj.get(workload, {}).get("k_ftl_step")
+            roofline["traffic_source"] = "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this command (%s)" % tj.get("_source", "profiles/")
         except Exception:
             pass
+    out = {"workload": workload, "value": value, "ms_per_step": ms / steps, "steps": steps, "roofline": roofline, "gpu_launches": int(launches),
+           "clocks": clocks, "S": S, "S_total": S_total, "N": N, "flags_s": flags_s, "cols_nbytes": int(cols.nbytes),
+           "implementation": {"scene_init": "reference scene frozen from Hair::Hair (tests/golden/c1_reference_scene.npz) + upload" if c1 else ("GPU (rvh_init_synthetic_head)" if device_init else "host (scenes.synthetic_head) + upload"),
+                              "parallelism": "strand-sharded x%d, grid exchange per step: %s" % (R.world, exchange) if R.world > 1 else "1 GPU",
+                              "strands_per_thread": int(sim.cfg.strands_per_thread),
+                              "step_n_fast_path": fast or "none",
+                              "head_sdf": ("%s lattice, cell %.3f, sampled through %s" % ("x".join(str(d) for d in sdf_lattice()[0]), SDF_CELL, sdf_mode)) if flags & rvh.SDF_ON else None}}
+    if not full:
+        sim.close()
+        return out
 
     # ---- end to end through the C ABI with HOST buffers ----------------------------------------
-    e2e = None
-    e2e_resident = None
     if not args.no_e2e:
-        barrier()
+        R.barrier(sim)
         sim.step_host_ptr(pinned.data_ptr(), aos_bytes, DT, 0.0)            # warm-up
-        barrier()
+        R.barrier(sim)
         t0 = time.perf_counter()
         for k in range(args.e2e_steps):
             sim.step_host_ptr(pinned.data_ptr(), aos_bytes, DT, DT * k)      # H2D Strand[S] + step + D2H Strand[S]
-        barrier()
-        el = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([el], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); el = float(t.item())
-        e2e = {"value": S_total * N * args.e2e_steps / el, "unit": UNIT,
-               "h2d_bytes_per_step": S * 32 * N + cols.nbytes + 8, "d2h_bytes_per_step": S * 32 * N,
-               "steps": args.e2e_steps, "what": "rvh_step_host: upload curvePoints+curveVels of the host Strand[S] AoS (pinned), one step, download them back, "
-                                                "every step (correctionVecs are dead across steps and stay on the host)"}
+        R.barrier(sim)
+        el = R.max(time.perf_counter() - t0)
+        out["e2e"] = {"value": S_total * N * args.e2e_steps / el, "unit": UNIT,
+                      "h2d_bytes_per_step": S * 32 * N + cols.nbytes + 8, "d2h_bytes_per_step": S * 32 * N,
+                      "steps": args.e2e_steps, "what": "rvh_step_host: upload curvePoints+curveVels of the host Strand[S] AoS (pinned), one step, download them back, "
+                                                       "every step (correctionVecs are dead across steps and stay on the host); above 128K strands the call pipelines "
+                                                       "chunked copies in both PCIe directions against the kernels (positions return before the grid is complete)"}
         # the reference's own per-frame contract: state stays on the GPU, only Time + Collider UBOs go in (Scene.cpp:78-87,133)
-        barrier()
-        n_res = min(args.steps, 50)
+        R.barrier(sim)
+        n_res = min(steps, 50)
         t0 = time.perf_counter()
         for k in range(n_res):
             sim.set_colliders(cols)
             sim.step(DT, DT * k)
             sim.draw_indirect()
-        barrier()
-        el = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([el], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); el = float(t.item())
-        e2e_resident = {"value": S_total * N * n_res / el, "unit": UNIT,
-                        "h2d_bytes_per_step": cols.nbytes + 8, "d2h_bytes_per_step": 16, "steps": n_res,
-                        "what": "per-frame API as the reference drives it: rvh_set_colliders (UBO) + rvh_step + rvh_draw_indirect read-back; strand state resident"}
-    expand = None
+        R.barrier(sim)
+        el = R.max(time.perf_counter() - t0)
+        out["e2e_resident"] = {"value": S_total * N * n_res / el, "unit": UNIT,
+                               "h2d_bytes_per_step": cols.nbytes + 8, "d2h_bytes_per_step": 16, "steps": n_res,
+                               "what": "per-frame API as the reference drives it: rvh_set_colliders (UBO) + rvh_step + rvh_draw_indirect read-back; strand state resident"}
     if args.expand:
         sim.expand(12, 42, download=False)                                   # allocation + tables
         times = [sim.expand(12, 42, download=False)[2] for _ in range(5)]
         verts = S * 12 * 43
         ems = statistics.median(times)
-        expand = {"isolines": 12, "divisions": 42, "vertices": verts, "ms": ems, "vertices_per_s": verts / (ems * 1e-3),
-                  "write_GBps": verts * 32 / (ems * 1e-3) / 1e9, "what": "k_expand_strands: 2 x float4 per vertex written, guide positions read once (per GPU)"}
+        out["expand"] = {"isolines": 12, "divisions": 42, "vertices": verts, "ms": ems, "vertices_per_s": verts / (ems * 1e-3),
+                         "write_GBps": verts * 32 / (ems * 1e-3) / 1e9, "what": "k_expand_strands: 2 x float4 per vertex written, guide positions read once (per GPU)"}
     sim.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="ns_full", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spt", type=int, default=0, help="strands per thread (0 auto)")
+    ap.add_argument("--flags", default=None, help="override the workload's feature flags, e.g. grid+windB (experiments)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE.json configurations appended as `configs`")
+    ap.add_argument("--no-checksum", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: every rank owns the workload's strand count; strong: the count is split over the ranks")
+    ap.add_argument("--no-kernel-events", action="store_true", help="time the steps without the per-kernel CUDA events (no roofline per-kernel split)")
+    ap.add_argument("--expand", action="store_true", help="also time the guide -> render strand expansion (hair.tesc/hair.tese, 12 isolines x 42 divisions) of the final state")
+    ap.add_argument("--device-init", action="store_true", help="generate the synthetic head on the GPU (rvh_init_synthetic_head) instead of uploading it")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import rvh_b200 as rvh
+    R = Ranks(rvh)
+    m = measure(R, rvh, args, args.workload, args.steps, args.warmup, args.scaling, full=True)
+
+    # ---- the other BASELINE.json configurations, time-capped, beside the headline ------------------
+    configs = None
+    if not args.no_configs and args.workload == "ns_full" and args.flags is None:
+        configs = []
+        if R.world == 1:
+            plan = [("c1", "weak"), ("c2", "weak"), ("c3", "weak"), ("c4", "weak"), ("c5", "weak")]
+        else:
+            plan = [("c4", "weak"), ("c5", "strong")]          # configs[3] and configs[4]: the multi-GPU ones
+        for w, sc in plan:
+            k = 100 if w in ("c1", "c2", "c3") else (40 if w == "c4" else 20)
+            c = measure(R, rvh, args, w, k, 3, sc, full=False)
+            r = c["roofline"]
+            configs.append({"workload": w, "scaling": sc, "strands_total": c["S_total"], "points_per_strand": c["N"], "features": c["flags_s"],
+                            "value": c["value"], "unit": UNIT, "ms_per_step": c["ms_per_step"], "steps": k, "roofline_frac": r["frac"],
+                            "step_frac": r["step_frac"], "per_kernel_ms": r["per_kernel_ms"], "gpu_launches": c["gpu_launches"],
+                            "step_n_fast_path": c["implementation"]["step_n_fast_path"]})
+    checksum = None if args.no_checksum else verification_checksum(R, rvh)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, el, info = time_reference(args.workload, flags_s, steps=2, warmup=1)
+    if R.rank == 0 and R.world == 1 and not args.no_cpu_baseline:
+        val, el, info = time_reference(args.workload, m["flags_s"], steps=3, warmup=1)
         cpu = dict(info, value=val, unit=UNIT, seconds=el)
 
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
+    if R.dist is not None:
+        R.dist.barrier()
+        R.dist.destroy_process_group()
+    if R.rank != 0:
         return 0
     out = {
-        "metric": "strand-point updates/sec", "value": value, "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "metric": "strand-point updates/sec", "value": m["value"], "unit": UNIT, "n_gpus": R.world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "strands_per_gpu": S, "strands_total": S_total, "points_per_strand": N,
-                   "scene_init": "reference scene frozen from Hair::Hair (tests/golden/c1_reference_scene.npz) + upload" if c1 else ("GPU (rvh_init_synthetic_head)" if device_init else "host (scenes.synthetic_head) + upload"),
-                   "dt": DT, "l2": "state %.0f MB per GPU > 126 MB L2, no flush needed" % (S * N * 24 / 1e6) if S * N * 24 > 126e6 else "state %.1f MB is L2-resident (launch/latency-bound config)" % (S * N * 24 / 1e6),
-                   "parallelism": "strand-sharded x%d, grid exchange per step: %s" % (world, exchange) if world > 1 else "1 GPU",
-                   "strands_per_thread": int(sim.cfg.strands_per_thread),
-                   "head_sdf": ("%s lattice, cell %.3f, sampled through %s" % ("x".join(str(d) for d in sdf_lattice()[0]), SDF_CELL, sdf_mode)) if flags & rvh.SDF_ON else None},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_resident,
-        "gpu_launches": int(launches), "clocks": clocks,
+        "config": workload_config(args, R.world), "implementation": m["implementation"],
+        "roofline": m["roofline"], "cpu_baseline": cpu, "e2e": m.get("e2e"), "e2e_resident": m.get("e2e_resident"),
+        "gpu_launches": m["gpu_launches"], "clocks": m["clocks"], "checksum": checksum, "configs": configs,
     }
-    if expand is not None:
-        out["expand"] = expand
+    if "expand" in m:
+        out["expand"] = m["expand"]
     print(json.dumps(out), flush=True)
     return 0
 

@@ -292,13 +292,16 @@ int launch_multi_step(rvh_ctx* ctx, int n, float dt, float& t) {      // t advan
         P.wind_tab[3 * k] = amp * s2T; P.wind_tab[3 * k + 1] = T3; P.wind_tab[3 * k + 2] = amp;
     }
     P.cta0 = 0;
+#define RVH_MULTI(V_, W_, NE_) k_ftl_step<V_, W_, NE_, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u)
+    const bool five = P.n_ell == 5;       // the reference scene's collider count: unrolled tests (the kernel is latency-bound here: the unrolled tests overlap)
     if (ctx->V == 2) {
-        if (wind) k_ftl_step<2, true, -1, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u);
-        else      k_ftl_step<2, false, -1, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u);
+        if (five) { if (wind) RVH_MULTI(2, true, 5); else RVH_MULTI(2, false, 5); }
+        else      { if (wind) RVH_MULTI(2, true, -1); else RVH_MULTI(2, false, -1); }
     } else {
-        if (wind) k_ftl_step<1, true, -1, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u);
-        else      k_ftl_step<1, false, -1, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u);
+        if (five) { if (wind) RVH_MULTI(1, true, 5); else RVH_MULTI(1, false, 5); }
+        else      { if (wind) RVH_MULTI(1, true, -1); else RVH_MULTI(1, false, -1); }
     }
+#undef RVH_MULTI
     P.multi_steps = 1;
     ctx->launches += 1;
     CU(cudaGetLastError());
