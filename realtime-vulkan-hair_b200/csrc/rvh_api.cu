@@ -104,6 +104,7 @@ struct rvh_ctx {
     unsigned* xflags = nullptr;           // [2][kMaxRanks] epochs + block counter, zero-initialised
     void* ipc_open[3 * kMaxRanks] = {};   // mappings to close
     unsigned epoch = 0;
+    long long exchange_timeout_cycles = 0;   // RVH_EXCHANGE_TIMEOUT_MS (default 5000) in SM clocks: bound of every wait on a peer in k_grid_exchange
     bool grid_reduced = true;             // the int64 accumulators hold the all-rank sum (NCCL path, or 1 rank)
     // timing
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -261,6 +262,15 @@ int launch_gather(rvh_ctx* ctx) {
 // Apply a deferred gather before anything reads velocities back.
 int flush_gather(rvh_ctx* ctx) { return ctx->gather_pending ? launch_gather(ctx) : RVH_OK; }
 
+// After the stream has been synchronised: did a k_grid_exchange give up waiting for a peer?
+int check_exchange_error(rvh_ctx* ctx) {
+    if (ctx->nranks <= 1 || !ctx->p2p || !ctx->xflags) return RVH_OK;
+    unsigned w = 0;
+    CU(cudaMemcpy(&w, ctx->xflags + kXErrWord, sizeof w, cudaMemcpyDeviceToHost));
+    if (w == 0) return RVH_OK;
+    return fail(ctx, RVH_ERR_NCCL, "grid exchange timed out waiting for rank " + std::to_string(w - 1) + " (a rank died or did not call rvh_step in lockstep); the state of this context is undefined");
+}
+
 int allreduce_grid(rvh_ctx* ctx) {
     if (ctx->grid_reduced) return RVH_OK;
     prof_begin(ctx, EV_AR);
@@ -357,7 +367,7 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
             prof_begin(ctx, EV_AR);
             ctx->epoch += 1;
             const int per = (cells + ctx->nranks - 1) / ctx->nranks;
-            k_grid_exchange<<<std::min((per + 255) / 256, 148), 256, 0, ctx->stream>>>(ctx->peers, ctx->rank, ctx->nranks, cells, ctx->P.int32_wrap, ctx->epoch);
+            k_grid_exchange<<<std::min((per + 255) / 256, 148), 256, 0, ctx->stream>>>(ctx->peers, ctx->rank, ctx->nranks, cells, ctx->P.int32_wrap, ctx->epoch, ctx->exchange_timeout_cycles);
             prof_end(ctx);
         } else {
             prof_begin(ctx, EV_FINALIZE);
@@ -429,6 +439,13 @@ void setup_peer_exchange(rvh_ctx* c) {
     } else ok = 0;
     cudaFree(dsend); cudaFree(drecv);
     c->p2p = ok != 0;
+    {
+        double ms = 5000.0;
+        if (const char* e = std::getenv("RVH_EXCHANGE_TIMEOUT_MS")) ms = std::max(1.0, std::atof(e));
+        int khz = 1965000;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->cfg.device);
+        c->exchange_timeout_cycles = (long long)(ms * (double)khz);
+    }
 }
 
 int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, const void* uid) {
@@ -696,7 +713,7 @@ int rvh_download_strands_aos(rvh_ctx* ctx, void* strands, size_t bytes) {
     if (r) return r;
     CU(cudaMemcpyAsync(strands, ctx->aos_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    return RVH_OK;
+    return check_exchange_error(ctx);
 }
 
 // ---- head SDF (extension) ---------------------------------------------------------------------------
@@ -1158,7 +1175,7 @@ int rvh_sync(rvh_ctx* ctx) {
     if (!ctx) return RVH_ERR_INVALID;
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaStreamSynchronize(ctx->stream));
-    return RVH_OK;
+    return check_exchange_error(ctx);
 }
 
 float rvh_last_step_ms(rvh_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }

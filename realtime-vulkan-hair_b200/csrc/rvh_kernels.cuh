@@ -1028,18 +1028,29 @@ constexpr int kMaxRanks = 8;
 struct ExchangePeers {
     const long long* grid[kMaxRanks];      // peers' raw int64 accumulators (read)
     float4* fgrid[kMaxRanks];              // peers' float grids (written)
-    unsigned* flags[kMaxRanks];            // peers' flag blocks: [2][kMaxRanks] epochs + [1] local block counter
+    unsigned* flags[kMaxRanks];            // peers' flag blocks: [2][kMaxRanks] epochs + [1] local block counter + [1] error word (kXErrWord)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
+// Every wait on a peer is bounded: a rank that died, or never reached this step, must surface as an error through the ABI
+// (RVH_ERR_NCCL from the next rvh_sync / read-back), not hang every GPU of the box.  On a timeout the waiting thread records
+// 1 + the peer's rank in the error word of its own flag block and carries on (the step's results are then meaningless).
+constexpr int kXErrWord = 2 * kMaxRanks + 1;
+__device__ __forceinline__ void wait_epoch(const unsigned* flag, unsigned epoch, long long timeout_cycles, unsigned* err, unsigned who) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        if (clock64() - t0 > timeout_cycles) { atomicMax(err, who + 1u); return; }
+    }
+}
+
 __global__ void __launch_bounds__(256)
-k_grid_exchange(const ExchangePeers X, int rank, int nranks, int cells, int int32_wrap, unsigned epoch) {
+k_grid_exchange(const ExchangePeers X, int rank, int nranks, int cells, int int32_wrap, unsigned epoch, long long timeout_cycles) {
     unsigned* my = X.flags[rank];
     // ---- barrier 1: every rank's splat is complete -----------------------------------------------
     if (blockIdx.x == 0 && threadIdx.x < nranks) st_release_sys(X.flags[threadIdx.x] + rank, epoch);
-    if (threadIdx.x < nranks) { while ((int)(ld_acquire_sys(my + threadIdx.x) - epoch) < 0) { } }
+    if (threadIdx.x < nranks) wait_epoch(my + threadIdx.x, epoch, timeout_cycles, my + kXErrWord, threadIdx.x);
     __syncthreads();
     // ---- reduce my slice over all peers, finalize, broadcast ---------------------------------------
     const int per = (cells + nranks - 1) / nranks;
@@ -1082,7 +1093,7 @@ k_grid_exchange(const ExchangePeers X, int rank, int nranks, int cells, int int3
         __syncthreads();
         if (threadIdx.x < nranks) {
             st_release_sys(X.flags[threadIdx.x] + kMaxRanks + rank, epoch);
-            while ((int)(ld_acquire_sys(my + kMaxRanks + threadIdx.x) - epoch) < 0) { }
+            wait_epoch(my + kMaxRanks + threadIdx.x, epoch, timeout_cycles, my + kXErrWord, threadIdx.x);
         }
     }
 }

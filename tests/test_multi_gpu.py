@@ -70,3 +70,45 @@ def test_two_gpu_sharded_equals_one_gpu(tmp_path, S, N, L, exchange):
     assert np.array_equal(parts[0]["grid"], parts[1]["grid"]), "ranks disagree on the reduced grid"
     assert np.array_equal(parts[0]["grid"], grid), "2-GPU grid differs from the 1-GPU grid"
     assert np.array_equal(sharded.view(np.uint32), single.view(np.uint32)), "2-GPU state differs from the 1-GPU state"
+
+
+def _lockstep_worker(rank, world, uid, out_dir):
+    """Rank 1 never steps: rank 0's fused grid exchange must give up after RVH_EXCHANGE_TIMEOUT_MS and report it."""
+    os.environ["RVH_GRID_EXCHANGE"] = "p2p"
+    os.environ["RVH_EXCHANGE_TIMEOUT_MS"] = "300"
+    sys.path.insert(0, ROOT)
+    import time
+    import rvh_b200 as rvh
+    S, N = 4096, 8
+    cols = rvh.scenes.bench_colliders()
+    lo, hi = rvh.scenes.shard_range(S, rank, world)
+    st = rvh.scenes.synthetic_head(hi - lo, N, 2.5, first_strand=lo, colliders=cols)
+    sim = rvh.HairSim(rvh.default_config(hi - lo, N, flags=rvh.GRID_ON, device=rank), rank=rank, nranks=world, nccl_id=uid)
+    sim.set_colliders(cols)
+    sim.upload(st)
+    res = {"mode": sim.exchange_mode(), "error": "", "seconds": 0.0}
+    if rank == 0:
+        t0 = time.perf_counter()
+        try:
+            sim.step(float(np.float32(1.0 / 60.0)), 0.0)
+            sim.sync()
+        except rvh.RvhError as e:
+            res["error"] = str(e)
+        res["seconds"] = time.perf_counter() - t0
+    else:
+        time.sleep(3.0)                                        # alive, but not stepping
+    np.savez(os.path.join(out_dir, "lock%d.npz" % rank), **res)
+    os._exit(0)                                                # the contexts are out of lockstep for good: no orderly teardown
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_a_rank_that_does_not_step_is_an_error_not_a_hang(tmp_path):
+    import torch.multiprocessing as tmp
+    import rvh_b200 as rvh
+    uid = rvh.nccl_unique_id()
+    tmp.spawn(_lockstep_worker, args=(2, uid, str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(str(tmp_path / "lock0.npz"))
+    if str(r0["mode"]) != "peer-memory-fused":
+        pytest.skip("peer mapping not available on this box: NCCL path (its own watchdog applies)")
+    assert "timed out waiting for rank 1" in str(r0["error"]), str(r0["error"])
+    assert float(r0["seconds"]) < 2.5
