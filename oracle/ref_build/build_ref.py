@@ -23,6 +23,10 @@ complete list; main()'s statements are untouched:
   R6  `void main()` -> `void shader_main()`
   R7  (only with --points N != 10) `#define NUM_CURVE_POINTS 10` -> N   [parameterised build]
   R8  (only with --wind A|B) un-comment the authors' wind line compute.comp:151 / :152
+hair.tese (oracle/_ref/libref_tese_N<N>.so, see ref_tese_tu.cpp) additionally needs its interface variables declared:
+  R9  drop `layout(isolines) in;`
+  R10 `layout(location = k) in vec4[][N] name;` -> `static vec4 (*name)[N];`; `layout(location = k) out T name;` -> `static T name;`
+  R11 parameter qualifier `out vec3 x` -> `vec3& x`
 """
 import argparse
 import os
@@ -96,6 +100,26 @@ def transliterate(src: str, points: int, wind: str) -> str:
     return "\n".join(fixed) + "\n"
 
 
+def transliterate_tese(src: str, points: int) -> str:
+    lines = []
+    for ln in src.split("\n"):
+        if re.match(r"^\s*layout\s*\(\s*isolines\s*\)\s*in\s*;", ln):                                   # R9
+            continue
+        m = re.match(r"^\s*layout\s*\(\s*location\s*=\s*\d+\s*\)\s*in\s+vec4\s*\[\s*\]\s*\[\s*(\w+)\s*\]\s*(\w+)\s*;", ln)
+        if m:                                                                                          # R10
+            lines.append("static vec4 (*%s)[%s];" % (m.group(2), m.group(1)))
+            continue
+        m = re.match(r"^\s*layout\s*\(\s*location\s*=\s*\d+\s*\)\s*out\s+(\w+)\s+(\w+)\s*;", ln)
+        if m:                                                                                          # R10
+            lines.append("static %s %s;" % (m.group(1), m.group(2)))
+            continue
+        if ln.lstrip().startswith("//layout"):
+            lines.append(ln)
+            continue
+        lines.append(re.sub(r"\bout\s+vec3\s+(\w+)", r"vec3& \1", ln))                                # R11
+    return transliterate("\n".join(lines), points, "")
+
+
 def run(cmd, out=None, deps=()):
     """Compile unless `out` is newer than every dependency."""
     if out and os.path.exists(out) and all(os.path.exists(d) and os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
@@ -141,6 +165,18 @@ def main():
             so = os.path.join(OUT, "libref_compute_%s.so" % tag)
             run([CXX] + CXXFLAGS + ["-I", gen_dir, "-I", glm_inc, os.path.join(HERE, "ref_compute_tu.cpp"), "-o", so],
                 out=so, deps=[gen, os.path.join(HERE, "ref_compute_tu.cpp")])
+    tese = open(os.path.join(src_dir, "shaders", "hair.tese")).read()
+    for n in (10, 16):
+        gen_dir = os.path.join(OUT, "gen", "tese_N%d" % n)
+        os.makedirs(gen_dir, exist_ok=True)
+        gen = os.path.join(gen_dir, "hair_tese.gen.inc")
+        text = transliterate_tese(tese, n)
+        if not os.path.exists(gen) or open(gen).read() != text:
+            with open(gen, "w") as f:
+                f.write(text)
+        so = os.path.join(OUT, "libref_tese_N%d.so" % n)
+        run([CXX] + CXXFLAGS + ["-I", gen_dir, "-I", glm_inc, os.path.join(HERE, "ref_tese_tu.cpp"), "-o", so],
+            out=so, deps=[gen, os.path.join(HERE, "ref_tese_tu.cpp")])
     return 0
 
 

@@ -564,3 +564,22 @@ def test_gpu_extension_modes_against_the_frozen_vectors():
     pw, tu, _ = sim.expand(4, 9)
     sim.close()
     assert np.abs(pw - g["exp_pw"]).max() <= 8e-6 and np.abs(tu - g["exp_tu"]).max() <= 2e-6
+
+
+@gpu
+def test_gpu_expansion_matches_the_reference_tese_text():
+    """k_expand_strands against the frozen outputs of hair.tese itself (tests/golden/expand_tese_n10.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "expand_tese_n10.npz"))
+    S, I, D = g["state"].shape[0], int(g["isolines"]), int(g["divisions"])
+    st = np.zeros((S, 3, 10, 4), np.float32)
+    st[:, 0:2] = g["state"]
+    sim = rvh.HairSim(rvh.default_config(S, 10, flags=0))
+    sim.upload(st)
+    pw, tu, _ = sim.expand(I, D)
+    sim.close()
+    ref = g["ref"]
+    assert np.abs(pw[:, :, :D, :3] - ref[..., :3]).max() <= 2e-6 * 4.0          # FMA contraction on the GPU: a few ulp of a coordinate of magnitude <= 4
+    assert np.abs(pw[:, :, :D, 3] - ref[..., 3]).max() <= 1e-7
+    assert np.abs(tu[:, :, :D, :3] - ref[..., 4:7]).max() <= 2e-6
+    assert np.array_equal(tu[:, :, :D, 3], ref[..., 7])

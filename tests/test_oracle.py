@@ -150,3 +150,54 @@ def test_live_ref_other_point_counts(golden_c1, tag, N):
         assert np.array_equal(bits(ref), bits(mine))
         assert np.array_equal(g.astype(np.int32), g_ref)
         st = ref
+
+
+# ---- guide -> render strand expansion: pinned by the reference's own hair.tese text -----------------------------------
+
+def _expand_golden():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "expand_tese_n10.npz"))
+    st = np.zeros((g["state"].shape[0], 3, 10, 4), np.float32)
+    st[:, 0:2] = g["state"]
+    return st, g["ref"], int(g["isolines"]), int(g["divisions"])
+
+
+def test_oracle_expansion_matches_the_reference_tese_text():
+    """orc_expand_strands against outputs of hair.tese itself (compiled as C++ against the reference's glm, frozen by
+    tests/golden/make_expand_golden.py): positions and widths BIT-exact, unit tangents to one ulp (the oracle divides by the
+    length, glm's normalize multiplies by inversesqrt).  The shader's fract(sin(.)) hashes are evaluated with the C library's
+    float sine there and with a double-precision sine here (so that CPU oracle and GPU agree, include/rvh.h); on these inputs the
+    two give the same float, hence the same hashes; the tolerance that would absorb a one-ulp sine difference is documented in
+    DESIGN.md section 9.  j = divisions (v = 1) is excluded: the shader reads curve point N there."""
+    st, ref, I, D = _expand_golden()
+    pw, tu = orc.expand_strands(st, I, D)
+    assert np.array_equal(bits(pw[:, :, :D, :3]), bits(ref[..., :3])), "positions differ from hair.tese"
+    assert np.array_equal(bits(pw[:, :, :D, 3]), bits(ref[..., 3])), "strand widths differ from hair.tese"
+    assert np.abs(tu[:, :, :D, :3] - ref[..., 4:7]).max() <= 1.2e-7
+    assert np.array_equal(bits(tu[:, :, :D, 3]), bits(ref[..., 7]))
+
+
+def test_oracle_expansion_matches_the_live_reference_tese_build():
+    import ctypes as C
+    import os
+    so = os.path.join(orc.REF_DIR, "libref_tese_N16.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    L = C.CDLL(so)
+    fp = C.POINTER(C.c_float)
+    L.ref_tese_eval.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]
+    assert L.ref_tese_num_curve_points() == 16
+    rng = np.random.default_rng(9)
+    S, N, I, D = 6, 16, 5, 17
+    st = np.zeros((S, 3, N, 4), np.float32)
+    st[:, 0, :, :3] = np.cumsum(rng.normal(scale=0.1, size=(S, N, 3)), axis=1).astype(np.float32) + rng.normal(size=(S, 1, 3)).astype(np.float32)
+    st[:, 0, :, 3] = 1
+    pw, tu = orc.expand_strands(st, I, D)
+    out = np.zeros(8, np.float32)
+    for s in range(S):
+        pts = np.ascontiguousarray(st[s, 0])
+        for k in range(I):
+            for j in range(D):
+                L.ref_tese_eval(pts.ctypes.data_as(fp), I, D, k, j, out.ctypes.data_as(fp))
+                assert np.array_equal(bits(pw[s, k, j]), bits(out[:4])), (s, k, j, pw[s, k, j], out[:4])
+                assert np.abs(tu[s, k, j, :3] - out[4:7]).max() <= 1.2e-7
