@@ -172,6 +172,21 @@ int rvh_expand_device_buffers(rvh_ctx* ctx, void** pos_width, void** tangent_u, 
  * keep it updated after every step in the reference's AoS vertex-buffer layout
  * (Renderer.cpp:2153-2161 binds it).  Needs a Vulkan device on the caller's side. */
 int rvh_import_strands_fd(rvh_ctx* ctx, int fd, size_t bytes);
+/* ... and the indirect-args VkBuffer vkCmdDrawIndirect reads (Hair::GetNumStrandsBuffer; Renderer.cpp:2240-2254 puts a buffer
+ * barrier on it): every step writes StrandDrawIndirect {S, 1, 0, 0} into it (the shader's own count, compute.comp:126-130, 302,
+ * ends at 32*ceil(S/32): include/rvh.h rvh_draw_indirect). */
+int rvh_import_indirect_fd(rvh_ctx* ctx, int fd, size_t bytes);
+/* A binary VkSemaphore exported with VK_KHR_external_semaphore_fd: every step signals it on the context's stream after its
+ * last write into the imported buffers, and the graphics submit waits on it.  This is the compute -> graphics ordering the
+ * reference does not have: Renderer::Frame submits the compute and the graphics command buffers to two queues with no
+ * semaphore between them (Renderer.cpp:2311-2345).  Without it the caller must rvh_sync() before the raster submit.
+ * The three import entry points need a Vulkan device on the caller's side; this image has none, so only their failure
+ * paths and -- through the hook below -- everything behind them are exercised by the tests. */
+int rvh_import_semaphore_fd(rvh_ctx* ctx, int fd);
+/* Test hook: stand-ins for the imported buffers.  strands_dev / indirect_dev are DEVICE pointers the caller owns (>= S*48*N and
+ * 16 bytes; NULL = none): every step then packs Strand[S] and writes the draw arguments into them exactly as it would into
+ * imported Vulkan memory. */
+int rvh_debug_set_interop_device_buffers(rvh_ctx* ctx, void* strands_dev, size_t strands_bytes, void* indirect_dev);
 
 /* vkQueueSubmit(Compute, computeCommandBuffer) in Renderer::Frame (Renderer.cpp:2311-2319):
  * grid clear + one pass of compute.comp.  dt / total_time are Scene::UpdateTime's values

@@ -16,7 +16,8 @@ EXPORTED_SYMBOLS = [
     "rvh_profile_enable", "rvh_profile_read", "rvh_sync", "rvh_last_step_ms", "rvh_kernel_launches",
     "rvh_last_error", "rvh_destroy", "rvh_collider_build", "rvh_collider_translate", "rvh_wind_fbm",
     "rvh_abi_version", "rvh_set_head_sdf", "rvh_bake_head_sdf_from_colliders", "rvh_bake_head_sdf_from_mesh",
-    "rvh_download_head_sdf", "rvh_sdf_mode", "rvh_debug_hit_masks", "rvh_expand_strands", "rvh_expand_device_buffers", "rvh_init_from_mesh", "rvh_download_collider_mask",
+    "rvh_download_head_sdf", "rvh_sdf_mode", "rvh_debug_hit_masks", "rvh_import_indirect_fd", "rvh_import_semaphore_fd",
+    "rvh_debug_set_interop_device_buffers", "rvh_expand_strands", "rvh_expand_device_buffers", "rvh_init_from_mesh", "rvh_download_collider_mask",
 ]
 
 
@@ -61,6 +62,9 @@ def load_library():
     L.rvh_upload_strands_aos.argtypes = [vp, vp, C.c_size_t]
     L.rvh_init_synthetic_head.argtypes = [vp, C.c_ulonglong, C.c_float, C.c_ulonglong]
     L.rvh_import_strands_fd.argtypes = [vp, C.c_int, C.c_size_t]
+    L.rvh_import_indirect_fd.argtypes = [vp, C.c_int, C.c_size_t]
+    L.rvh_import_semaphore_fd.argtypes = [vp, C.c_int]
+    L.rvh_debug_set_interop_device_buffers.argtypes = [vp, vp, C.c_size_t, vp]
     L.rvh_step.argtypes = [vp, C.c_float, C.c_float]
     L.rvh_step_n.argtypes = [vp, C.c_int, C.c_float, C.c_float, fp]
     L.rvh_step_host.argtypes = [vp, vp, C.c_size_t, C.c_float, C.c_float]
@@ -91,6 +95,7 @@ def load_library():
     L.rvh_bake_head_sdf_from_mesh.argtypes = [vp, fp, C.c_int, ip, C.c_int, ip, fp, C.c_float]
     L.rvh_download_head_sdf.argtypes = [vp, fp, C.c_size_t]
     L.rvh_sdf_mode.argtypes = [vp]
+    L.rvh_debug_hit_masks.argtypes = [vp, C.POINTER(C.c_ubyte), C.c_size_t]
     L.rvh_download_collider_mask.argtypes = [vp, C.POINTER(C.c_ubyte), C.c_size_t, ip]
     L.rvh_expand_strands.argtypes = [vp, C.c_int, C.c_int, fp, fp, C.c_size_t, fp]
     L.rvh_init_from_mesh.argtypes = [vp, fp, fp, C.c_int, C.c_ulonglong, C.c_float, C.c_ulonglong]

@@ -68,8 +68,11 @@ struct rvh_ctx {
     bool perm_active = false;             // the planes currently hold the strands in `perm` order (false: external order)
     void* aos_dev = nullptr;              // Strand[S] staging / interop target
     size_t aos_bytes = 0;
-    void* interop_aos = nullptr;          // imported VkBuffer memory (rvh_import_strands_fd)
+    void* interop_aos = nullptr;          // imported VkBuffer memory (rvh_import_strands_fd), or a caller-owned device buffer (test hook)
     cudaExternalMemory_t interop_mem = nullptr;
+    uint32_t* interop_indirect = nullptr; // imported StrandDrawIndirect buffer (rvh_import_indirect_fd), or caller-owned (test hook)
+    cudaExternalMemory_t interop_indirect_mem = nullptr;
+    cudaExternalSemaphore_t interop_sem = nullptr;   // signalled after the step's writes into the imported buffers (rvh_import_semaphore_fd)
     void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     unsigned* sort_keys = nullptr; unsigned* sort_keys_out = nullptr; int* sort_ids = nullptr;
     StepParams P;
@@ -379,6 +382,11 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
         ctx->gather_pending = true;
         if (!lazy || ctx->interop_aos) { int r = launch_gather(ctx); if (r) return r; }
     }
+    if (ctx->interop_indirect) {                                        // compute.comp:126-130,302: the draw's vertexCount = strands
+        k_write_indirect<<<1, 32, 0, ctx->stream>>>(ctx->interop_indirect, (uint32_t)ctx->S);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+    }
     if (ctx->interop_aos) {
         const int tiles = (ctx->S + kTile - 1) / kTile;
         const size_t sm = (size_t)9 * ctx->N * (kTile + 1) * sizeof(float);
@@ -386,6 +394,10 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
         k_pack_aos<<<tiles, 256, sm, ctx->stream>>>((float4*)ctx->interop_aos, ctx->planes, ctx->corr, ctx->perm_active ? ctx->perm : nullptr, ctx->S, ctx->S_pad, ctx->N, 0, 7);
         ctx->launches += 1;
         CU(cudaGetLastError());
+    }
+    if (ctx->interop_sem) {                                             // the graphics submit waits on this (VK_KHR_external_semaphore)
+        cudaExternalSemaphoreSignalParams sp; std::memset(&sp, 0, sizeof sp);
+        CU(cudaSignalExternalSemaphoresAsync(&ctx->interop_sem, &sp, 1, ctx->stream));
     }
     return RVH_OK;
 }
@@ -952,6 +964,48 @@ int rvh_import_strands_fd(rvh_ctx* ctx, int fd, size_t bytes) {
     return RVH_OK;
 }
 
+int rvh_import_indirect_fd(rvh_ctx* ctx, int fd, size_t bytes) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (bytes < 16) return fail(ctx, RVH_ERR_INVALID, "imported buffer smaller than StrandDrawIndirect (16 bytes)");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (ctx->interop_indirect_mem) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->interop_indirect) cudaFree(ctx->interop_indirect);
+        cudaDestroyExternalMemory(ctx->interop_indirect_mem);
+        ctx->interop_indirect = nullptr; ctx->interop_indirect_mem = nullptr;
+    }
+    cudaExternalMemoryHandleDesc hd; std::memset(&hd, 0, sizeof hd);
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd; hd.handle.fd = fd; hd.size = bytes;
+    CU(cudaImportExternalMemory(&ctx->interop_indirect_mem, &hd));
+    cudaExternalMemoryBufferDesc bd; std::memset(&bd, 0, sizeof bd);
+    bd.offset = 0; bd.size = bytes;
+    void* p = nullptr;
+    CU(cudaExternalMemoryGetMappedBuffer(&p, ctx->interop_indirect_mem, &bd));
+    ctx->interop_indirect = (uint32_t*)p;
+    return RVH_OK;
+}
+
+int rvh_import_semaphore_fd(rvh_ctx* ctx, int fd) {
+    if (!ctx) return RVH_ERR_INVALID;
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (ctx->interop_sem) { CU(cudaStreamSynchronize(ctx->stream)); cudaDestroyExternalSemaphore(ctx->interop_sem); ctx->interop_sem = nullptr; }
+    cudaExternalSemaphoreHandleDesc sd; std::memset(&sd, 0, sizeof sd);
+    sd.type = cudaExternalSemaphoreHandleTypeOpaqueFd; sd.handle.fd = fd;
+    CU(cudaImportExternalSemaphore(&ctx->interop_sem, &sd));
+    return RVH_OK;
+}
+
+int rvh_debug_set_interop_device_buffers(rvh_ctx* ctx, void* strands_dev, size_t strands_bytes, void* indirect_dev) {
+    if (!ctx) return RVH_ERR_INVALID;
+    if (ctx->interop_mem || ctx->interop_indirect_mem) return fail(ctx, RVH_ERR_STATE, "imported Vulkan buffers are in use");
+    if (strands_dev && strands_bytes < ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "strands buffer smaller than Strand[S]");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->interop_aos = strands_dev;                                  // caller-owned: never freed here (interop_mem stays null)
+    ctx->interop_indirect = (uint32_t*)indirect_dev;
+    return RVH_OK;
+}
+
 int rvh_step(rvh_ctx* ctx, float dt, float total_time) {
     if (!ctx) return RVH_ERR_INVALID;
     CU(cudaSetDevice(ctx->cfg.device));
@@ -1189,8 +1243,9 @@ void rvh_destroy(rvh_ctx* c) {
     for (void* q : c->ipc_open) if (q) cudaIpcCloseMemHandle(q);
     cudaFree(c->xflags);
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    if (c->interop_aos) cudaFree(c->interop_aos);
-    if (c->interop_mem) cudaDestroyExternalMemory(c->interop_mem);
+    if (c->interop_mem) { if (c->interop_aos) cudaFree(c->interop_aos); cudaDestroyExternalMemory(c->interop_mem); }
+    if (c->interop_indirect_mem) { if (c->interop_indirect) cudaFree(c->interop_indirect); cudaDestroyExternalMemory(c->interop_indirect_mem); }
+    if (c->interop_sem) cudaDestroyExternalSemaphore(c->interop_sem);
     cudaFree(c->cmask_dev);
     cudaFree(c->sdf_dev); cudaFree(c->bake_tris); cudaFree(c->exp_tab); cudaFree(c->exp_pw); cudaFree(c->exp_tu);
     cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->fgrid); cudaFree(c->perm); cudaFree(c->aos_dev);

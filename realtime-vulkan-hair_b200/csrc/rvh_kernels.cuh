@@ -1119,6 +1119,12 @@ k_grid_gather(const __grid_constant__ StepParams P, float* __restrict__ planes, 
     }
 }
 
+// StrandDrawIndirect of the imported indirect-args buffer (Strand.h:53-58): {vertexCount = S, instanceCount = 1, 0, 0}.  The shader
+// zeroes vertexCount and lets every invocation add 1 (compute.comp:126-130, 302); the value it ends with is the invocation count.
+__global__ void k_write_indirect(uint32_t* __restrict__ out, uint32_t strands) {
+    if (threadIdx.x < 4) out[threadIdx.x] = threadIdx.x == 0 ? strands : (threadIdx.x == 1 ? 1u : 0u);
+}
+
 // ---- test hook: the collider decisions of compute.comp:158-180 as THIS path takes them ------------------------------------
 // One byte per point (external strand order, [S][N]): bit 0 = inside the sphere (:162), bit j = inside ellipsoid j (:66), or,
 // with the head SDF, bit 1 = trilinear distance < 0.  Same device functions, same operations as point_update, so the byte is

@@ -194,7 +194,9 @@ Hair::Hair(Device*, VkCommandPool, std::vector<float> aos, int S, int N) : numSt
 
 // ---- Scene ---------------------------------------------------------------------------------------------
 Scene::Scene(Device* device, VkCommandPool, std::vector<Collider> colliders, std::vector<Model*> models)
-    : device(device), models(std::move(models)), colliders(std::move(colliders)) {}
+    : device(device), models(std::move(models)), colliders(std::move(colliders)) {
+    grid.assign((size_t)64 * 64 * 64, GridCell(ivec3{ 0, 0, 0 }, 0));                  // Scene.cpp:16-20: GRID_DIM^3 zero cells
+}
 
 void Scene::UpdateTime() {
     if (fixedDt > 0.0f) {
@@ -252,6 +254,8 @@ void Renderer::CreateComputePipeline() {
         const std::vector<float>& st = h->GetInitialStrands();
         check(rvh_upload_strands_aos(ctx, st.data(), st.size() * sizeof(float)), ctx, "Failed to upload strands");
         if (h->exportedFd >= 0) check(rvh_import_strands_fd(ctx, h->exportedFd, h->exportedBytes), ctx, "Failed to import strands buffer");
+        if (h->exportedIndirectFd >= 0) check(rvh_import_indirect_fd(ctx, h->exportedIndirectFd, h->exportedIndirectBytes), ctx, "Failed to import indirect-args buffer");
+        if (h->exportedSemaphoreFd >= 0) check(rvh_import_semaphore_fd(ctx, h->exportedSemaphoreFd), ctx, "Failed to import semaphore");
     }
 }
 
@@ -264,6 +268,9 @@ void Renderer::RecordComputeCommandBuffer() {
 void Renderer::Frame() {
     const Time& t = scene->GetTime();
     const std::vector<Collider>& cols = scene->GetColliders();
+    // Scene::UpdateTime's wall-clock delta can be zero (two frames inside one clock tick).  The shader would divide by it
+    // (compute.comp:195, 214: NaN velocities); this path leaves the state untouched for such a frame instead of failing it.
+    if (!(t.deltaTime > 0.0f)) return;
     for (rvh_ctx* ctx : contexts) {
         // the collider and time UBOs are persistently mapped in the reference (Scene.cpp:10-13,86,133):
         // whatever the host wrote last is what the dispatch reads

@@ -95,7 +95,14 @@ public:
     const StrandDrawIndirect& GetIndirectDraw() const { return indirectDraw; }
     // Interop build: the caller exports strandsBuffer's memory (VK_KHR_external_memory_fd) and hands the fd over.
     void SetExportedStrandsMemory(VkBuffer buffer, int fd, size_t bytes) { strandsBuffer = buffer; exportedFd = fd; exportedBytes = bytes; }
+    // ... likewise the indirect-args buffer (Renderer.cpp:2240-2254 barriers it before vkCmdDrawIndirect) and a binary semaphore
+    // (VK_KHR_external_semaphore_fd) that the compute step signals and the graphics submit waits on: the compute -> graphics
+    // ordering the reference leaves out (Renderer.cpp:2311-2345 submits both queues with no semaphore in between)
+    void SetExportedIndirectMemory(VkBuffer buffer, int fd, size_t bytes) { numStrandsBuffer = buffer; exportedIndirectFd = fd; exportedIndirectBytes = bytes; }
+    void SetExportedSemaphore(int fd) { exportedSemaphoreFd = fd; }
     int exportedFd = -1; size_t exportedBytes = 0;
+    int exportedIndirectFd = -1; size_t exportedIndirectBytes = 0;
+    int exportedSemaphoreFd = -1;
 private:
     void buildFromFollicles(const std::vector<vec3>& roots, const std::vector<vec3>& normals);
     VkBuffer strandsBuffer = nullptr, numStrandsBuffer = nullptr, modelBuffer = nullptr;
@@ -108,10 +115,23 @@ class Scene {
 public:
     Scene() = delete;
     Scene(Device* device, VkCommandPool commandPool, std::vector<Collider> colliders, std::vector<Model*> models);   // Scene.h:83
+    const std::vector<Model*>& GetModels() const { return models; }                // Scene.h:88
     const std::vector<Hair*>& GetHair() const { return hair; }
     const std::vector<Collider>& GetColliders() const { return colliders; }
+    // Scene.h:91: the host copy of the grid the reference uploads once, all zero (Scene.cpp:16-20); the live grid is device memory
+    const std::vector<GridCell>& GetGrid() const { return grid; }
+    void AddModel(Model* m) { models.push_back(m); }                                // Scene.h:94
     void AddHair(Hair* h) { hair.push_back(h); }
     void AddCollider(Collider c) { colliders.push_back(c); }
+    // Scene.h:98-101.  In the reference these are the VkBuffers behind descriptor sets 1-3 of the compute pipeline
+    // (Renderer.cpp:836-997).  Here the time and collider UBOs are arguments of rvh_step / rvh_set_colliders and the grid is
+    // owned by the rvh context, so the handles stay VK_NULL_HANDLE unless an interop build registers its own (SetVulkanBuffers);
+    // nothing in the compute path reads them.
+    VkBuffer GetTimeBuffer() const { return timeBuffer; }
+    VkBuffer GetCollidersBuffer() const { return collidersBuffer; }
+    VkBuffer GetGridBuffer() const { return gridBuffer; }
+    VkBuffer GetModelBuffer() const { return modelBuffer; }
+    void SetVulkanBuffers(VkBuffer time, VkBuffer colliders, VkBuffer grid, VkBuffer model) { timeBuffer = time; collidersBuffer = colliders; gridBuffer = grid; modelBuffer = model; }
     void UpdateTime();                                  // Scene.cpp:78-87: wall clock unless a fixed step is set
     void translateSphere(vec3 translation);             // Scene.cpp:110-136 (collider half)
     const Time& GetTime() const { return time; }
@@ -123,6 +143,8 @@ private:
     std::vector<Model*> models;
     std::vector<Hair*> hair;
     std::vector<Collider> colliders;
+    std::vector<GridCell> grid;
+    VkBuffer timeBuffer = nullptr, collidersBuffer = nullptr, gridBuffer = nullptr, modelBuffer = nullptr;
     float fixedDt = 0.0f;
     std::chrono::high_resolution_clock::time_point startTime = std::chrono::high_resolution_clock::now();
 };

@@ -215,3 +215,37 @@ def test_pipelined_step_host_equals_upload_step_download(S, N, L, flags):
     assert np.array_equal(bits(buf[:, 0:2]), bits(ref[:, 0:2]))
     assert np.all(buf[:, 2] == 123.0)
     assert np.array_equal(bits(again[:, 0:2]), bits(ref[:, 0:2]))
+
+
+def test_interop_pack_and_indirect_args_land_in_external_device_buffers():
+    """Everything behind rvh_import_strands_fd / rvh_import_indirect_fd except the import itself (no Vulkan device here): with
+    caller-owned device buffers standing in for the imported VkBuffers, every rvh_step must leave the reference's vertex-buffer
+    layout Strand[S] (Strand.h:11-15, curvePoints first) and StrandDrawIndirect {S,1,0,0} in them -- the same bytes
+    rvh_download_strands_aos returns, gather applied."""
+    import torch
+    S, N, L = 5000, 10, 2.5
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, L, colliders=cols)
+    ext = torch.full((S * 3 * N * 4,), 7.0, dtype=torch.float32, device="cuda")
+    ind = torch.full((4,), 99, dtype=torch.int32, device="cuda")
+    sim = rvh.HairSim(rvh.default_config(S, N, flags=rvh.GRID_ON | rvh.WIND_B | rvh.KEEP_CORRECTION))
+    sim.set_colliders(cols)
+    sim.upload(st)
+    assert sim.L.rvh_debug_set_interop_device_buffers(sim.ctx, ext.data_ptr(), ext.numel() * 4, ind.data_ptr()) == 0
+    for k in range(3):
+        sim.step(DT, 0.1 * k)
+        sim.sync()
+        got = ext.cpu().numpy().reshape(S, 3, N, 4)
+        want = sim.download()
+        assert np.array_equal(bits(got), bits(want)), "step %d: external Strand[S] differs from the download" % k
+        assert ind.cpu().tolist() == [S, 1, 0, 0]
+    assert sim.L.rvh_debug_set_interop_device_buffers(sim.ctx, None, 0, None) == 0
+    sim.step(DT, 0.3)
+    sim.sync()
+    assert np.array_equal(bits(ext.cpu().numpy().reshape(S, 3, N, 4)), bits(want))      # detached: untouched
+    # the import entry points themselves: bogus handles are errors, not crashes, and leave the context usable
+    assert sim.L.rvh_import_indirect_fd(sim.ctx, -1, 16) < 0 and sim.L.rvh_last_error(sim.ctx)
+    assert sim.L.rvh_import_indirect_fd(sim.ctx, 0, 8) == -1
+    assert sim.L.rvh_import_semaphore_fd(sim.ctx, -1) < 0
+    sim.step(DT, 0.4)
+    sim.close()
