@@ -321,6 +321,27 @@ int launch_multi_step(rvh_ctx* ctx, int n, float dt, float& t) {      // t advan
     return RVH_OK;
 }
 
+// The step's grid is complete on this rank: make the float grid the gather reads (compute.comp:276-286), summed over the ranks.
+int finalize_grid(rvh_ctx* ctx) {
+    const int cells = ctx->P.G * ctx->P.G * ctx->P.G;
+    if (ctx->nranks > 1 && ctx->p2p && !ctx->grid_reduced) {
+        // reduce-scatter + finalize + all-gather in one kernel over NVLink peer memory (every rank calls in lockstep)
+        prof_begin(ctx, EV_AR);
+        ctx->epoch += 1;
+        const int per = (cells + ctx->nranks - 1) / ctx->nranks;
+        k_grid_exchange<<<std::min((per + 255) / 256, 148), 256, 0, ctx->stream>>>(ctx->peers, ctx->rank, ctx->nranks, cells, ctx->P.int32_wrap, ctx->epoch, ctx->exchange_timeout_cycles);
+        prof_end(ctx);
+    } else {
+        prof_begin(ctx, EV_FINALIZE);
+        k_grid_finalize<<<(cells + 255) / 256, 256, 0, ctx->stream>>>((const long long*)ctx->grid, ctx->fgrid, cells, ctx->P.int32_wrap);
+        prof_end(ctx);
+    }
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    ctx->gather_pending = true;
+    return RVH_OK;
+}
+
 // phases: bit 0 = integrate + FTL (+ splat, all-reduce), bit 1 = grid finalize + gather.
 // lazy: leave the gather to the next step's k_ftl_step (steady-state stepping); otherwise run it now.
 int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
@@ -364,22 +385,7 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
         }
     }
     if ((phases & 2) && grid) {
-        const int cells = ctx->P.G * ctx->P.G * ctx->P.G;
-        if (ctx->nranks > 1 && ctx->p2p && !ctx->grid_reduced) {
-            // reduce-scatter + finalize + all-gather in one kernel over NVLink peer memory (every rank calls in lockstep)
-            prof_begin(ctx, EV_AR);
-            ctx->epoch += 1;
-            const int per = (cells + ctx->nranks - 1) / ctx->nranks;
-            k_grid_exchange<<<std::min((per + 255) / 256, 148), 256, 0, ctx->stream>>>(ctx->peers, ctx->rank, ctx->nranks, cells, ctx->P.int32_wrap, ctx->epoch, ctx->exchange_timeout_cycles);
-            prof_end(ctx);
-        } else {
-            prof_begin(ctx, EV_FINALIZE);
-            k_grid_finalize<<<(cells + 255) / 256, 256, 0, ctx->stream>>>((const long long*)ctx->grid, ctx->fgrid, cells, ctx->P.int32_wrap);
-            prof_end(ctx);
-        }
-        ctx->launches += 1;
-        CU(cudaGetLastError());
-        ctx->gather_pending = true;
+        { int r = finalize_grid(ctx); if (r) return r; }
         if (!lazy || ctx->interop_aos) { int r = launch_gather(ctx); if (r) return r; }
     }
     if (ctx->interop_indirect) {                                        // compute.comp:126-130,302: the draw's vertexCount = strands
@@ -1131,11 +1137,11 @@ static int step_host_pipelined(rvh_ctx* ctx, void* strands, float dt, float tota
         if (ne > 0) CU(cudaMemcpy2DAsync(host + (size_t)s0 * pitch, pitch, dev + (size_t)s0 * pitch, pitch, grid ? third : 2 * third, ne, cudaMemcpyDeviceToHost, ctx->d2h_stream));
     }
     if (grid) {
-        const int cells = P.G * P.G * P.G;
-        k_grid_finalize<<<(cells + 255) / 256, 256, 0, ctx->stream>>>((const long long*)ctx->grid, ctx->fgrid, cells, P.int32_wrap);
-        ctx->launches += 1;
-        CU(cudaGetLastError());
-        ctx->gather_pending = true;
+        if (ctx->nranks > 1) {                                             // every rank calls rvh_step_host in lockstep, like rvh_step
+            ctx->grid_reduced = false;
+            if (!ctx->p2p) { int r = allreduce_grid(ctx); if (r) return r; }
+        }
+        { int r = finalize_grid(ctx); if (r) return r; }
         { int r = launch_gather(ctx); if (r) return r; }
         for (int c = 0; c < nchunks; ++c) {
             const int s0 = c * chunk, ns = std::min(chunk, ctx->S_pad - s0), ne = std::max(0, std::min(ns, ctx->S - s0));
@@ -1151,13 +1157,13 @@ static int step_host_pipelined(rvh_ctx* ctx, void* strands, float dt, float tota
     }
     CU(cudaStreamSynchronize(ctx->d2h_stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    return RVH_OK;
+    return check_exchange_error(ctx);
 }
 
 int rvh_step_host(rvh_ctx* ctx, void* strands, size_t bytes, float dt, float total_time) {
     if (!ctx) return RVH_ERR_INVALID;
     if (!strands || bytes != ctx->aos_bytes) return fail(ctx, RVH_ERR_INVALID, "strands must be S*48*N bytes");
-    if (ctx->colliders_set && dt > 0.f && !ctx->corr && !ctx->interop_aos && ctx->nranks == 1 && ctx->S >= 131072 && !(ctx->cfg.flags & RVH_SDF_TMA) &&
+    if (ctx->colliders_set && dt > 0.f && !ctx->corr && !ctx->interop_aos && ctx->S >= 131072 && !(ctx->cfg.flags & RVH_SDF_TMA) &&
         !((ctx->cfg.flags & RVH_SDF_ON) && !ctx->sdf_dev) && !std::getenv("RVH_NO_HOST_PIPE")) {
         CU(cudaSetDevice(ctx->cfg.device));
         return step_host_pipelined(ctx, strands, dt, total_time);

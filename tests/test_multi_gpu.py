@@ -112,3 +112,42 @@ def test_a_rank_that_does_not_step_is_an_error_not_a_hang(tmp_path):
         pytest.skip("peer mapping not available on this box: NCCL path (its own watchdog applies)")
     assert "timed out waiting for rank 1" in str(r0["error"]), str(r0["error"])
     assert float(r0["seconds"]) < 2.5
+
+
+def _host_worker(rank, world, uid, S, N, L, out_dir):
+    os.environ["RVH_GRID_EXCHANGE"] = "p2p"
+    sys.path.insert(0, ROOT)
+    import rvh_b200 as rvh
+    dt = float(np.float32(1.0 / 60.0))
+    cols = rvh.scenes.bench_colliders()
+    lo, hi = rvh.scenes.shard_range(S, rank, world)
+    buf = rvh.scenes.synthetic_head(hi - lo, N, L, first_strand=lo, colliders=cols)
+    rest = float(np.float32(L) / np.float32(N - 1))
+    sim = rvh.HairSim(rvh.default_config(hi - lo, N, flags=rvh.GRID_ON | rvh.WIND_B, device=rank, rest_length=rest), rank=rank, nranks=world, nccl_id=uid)
+    sim.set_colliders(cols)
+    sim.step_host(buf, dt, 0.3)                                 # pipelined (>= 128K strands per rank), grid exchange inside
+    sim.step_host(buf, dt, 0.3 + dt)
+    sim.close()
+    np.savez(os.path.join(out_dir, "host%d.npz" % rank), state=buf)
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_two_gpu_pipelined_step_host_equals_one_gpu(tmp_path):
+    """rvh_step_host's chunk pipeline on sharded contexts: two ranks x 140K strands, two host round trips, against one GPU."""
+    import torch.multiprocessing as tmp
+    import rvh_b200 as rvh
+    S, N, L = 280000, 8, 0.4
+    uid = rvh.nccl_unique_id()
+    tmp.spawn(_host_worker, args=(2, uid, S, N, L, str(tmp_path)), nprocs=2, join=True)
+    sharded = np.concatenate([np.load(str(tmp_path / ("host%d.npz" % r)))["state"] for r in range(2)])
+    dt = float(np.float32(1.0 / 60.0))
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, L, colliders=cols)
+    sim = rvh.HairSim(rvh.default_config(S, N, flags=rvh.GRID_ON | rvh.WIND_B, rest_length=float(np.float32(L) / np.float32(N - 1))))
+    sim.set_colliders(cols)
+    for k in range(2):
+        sim.upload(st)
+        sim.step(dt, 0.3 + k * dt)
+        st = sim.download()
+    sim.close()
+    assert np.array_equal(sharded[:, 0:2].view(np.uint32), st[:, 0:2].view(np.uint32))
