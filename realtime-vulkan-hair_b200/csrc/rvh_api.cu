@@ -66,6 +66,7 @@ struct rvh_ctx {
     size_t grid_bytes = 0;
     int* perm = nullptr;                  // internal -> external strand index (Morton order)
     bool perm_active = false;             // the planes currently hold the strands in `perm` order (false: external order)
+    bool needs_resort = false;            // rvh_step_host's pipeline left the strands in the caller's order: Morton-sort them before the next resident step
     void* aos_dev = nullptr;              // Strand[S] staging / interop target
     size_t aos_bytes = 0;
     void* interop_aos = nullptr;          // imported VkBuffer memory (rvh_import_strands_fd), or a caller-owned device buffer (test hook)
@@ -342,12 +343,26 @@ int finalize_grid(rvh_ctx* ctx) {
     return RVH_OK;
 }
 
+}  // namespace
+extern "C" {
+static int unpack_from_staging(rvh_ctx* ctx);
+static int pack_to_staging(rvh_ctx* ctx);
+}
+namespace {
+
 // phases: bit 0 = integrate + FTL (+ splat, all-reduce), bit 1 = grid finalize + gather.
 // lazy: leave the gather to the next step's k_ftl_step (steady-state stepping); otherwise run it now.
 int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
     if (!ctx->uploaded) return fail(ctx, RVH_ERR_STATE, "rvh_step before rvh_upload_strands_aos");
     if (!ctx->colliders_set) return fail(ctx, RVH_ERR_STATE, "rvh_step before rvh_set_colliders");
     if (!(dt > 0.f)) return fail(ctx, RVH_ERR_INVALID, "dt must be > 0");
+    if (ctx->needs_resort) {
+        // the last state arrived through rvh_step_host's chunk pipeline, in the caller's strand order: restore the Morton order the
+        // splat's warp aggregation lives on (device-side: pack to the staging buffer, sort the roots, unpack) before stepping on
+        ctx->needs_resort = false;
+        { int r = pack_to_staging(ctx); if (r) return r; }
+        { int r = unpack_from_staging(ctx); if (r) return r; }
+    }
     StepParams& P = ctx->P;
     P.dt = dt; P.inv_dt = 1.0f / dt; P.dt2 = dt * dt; P.vel_scale = P.damping / dt;
     const int flags = ctx->cfg.flags;
@@ -642,6 +657,7 @@ static int unpack_from_staging(rvh_ctx* ctx) {
     CU(cudaGetLastError());
     ctx->launches += reorder ? 3 : 1;
     ctx->uploaded = true;
+    ctx->needs_resort = false;
     ctx->perm_active = reorder;
     ctx->state_version += 1;
     ctx->gather_pending = false;          // new state: nothing of the old grid applies to it
@@ -1120,6 +1136,7 @@ static int step_host_pipelined(rvh_ctx* ctx, void* strands, float dt, float tota
     if (grid) CU(cudaMemsetAsync(ctx->grid, 0, ctx->grid_bytes, ctx->stream));      // Renderer.cpp:2063
     ctx->k1_clear = nullptr; ctx->k1_clear_n = 0;
     ctx->perm_active = false; ctx->gather_pending = false; ctx->uploaded = true; ctx->state_version += 1;
+    ctx->needs_resort = !(flags & RVH_KEEP_ORDER) && ctx->S >= 1024;
     for (int c = 0; c < nchunks; ++c) {
         const int s0 = c * chunk, ns = std::min(chunk, ctx->S_pad - s0), ne = std::max(0, std::min(ns, ctx->S - s0));
         cudaEvent_t ev_in = ctx->pipe_ev[3 * c], ev_pos = ctx->pipe_ev[3 * c + 1];

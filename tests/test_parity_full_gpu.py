@@ -249,3 +249,26 @@ def test_interop_pack_and_indirect_args_land_in_external_device_buffers():
     assert sim.L.rvh_import_semaphore_fd(sim.ctx, -1) < 0
     sim.step(DT, 0.4)
     sim.close()
+
+
+def test_resident_steps_after_a_pipelined_host_step_run_on_morton_order_again():
+    """The chunk pipeline leaves the strands in the caller's order; the next resident step must restore the Morton order (the
+    splat's warp aggregation depends on it: ~10x slower otherwise) without changing a bit of the result."""
+    S, N, L = 200000, 16, 2.5
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, L, colliders=cols)
+    flags = rvh.GRID_ON | rvh.WIND_B
+    a = rvh.HairSim(rvh.default_config(S, N, flags=flags)); a.set_colliders(cols)
+    buf = st.copy()
+    a.step_host(buf, DT, 0.1)
+    ms_a = a.step_n(20, DT, 0.2) / 20
+    fa = a.download()
+    a.close()
+    b = _fresh(S, N, L, flags, st, cols)
+    b.step(DT, 0.1)
+    b.upload(b.download())
+    ms_b = b.step_n(20, DT, 0.2) / 20
+    fb = b.download()
+    b.close()
+    assert np.array_equal(bits(fa[:, 0:2]), bits(fb[:, 0:2]))
+    assert ms_a <= 1.5 * ms_b + 0.05, "resident steps after rvh_step_host are slow: %.3f ms vs %.3f ms" % (ms_a, ms_b)
