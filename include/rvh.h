@@ -193,13 +193,20 @@ int rvh_debug_set_interop_device_buffers(rvh_ctx* ctx, void* strands_dev, size_t
  * (Scene.cpp:78-87).  Asynchronous on the context's stream. */
 int rvh_step(rvh_ctx* ctx, float dt, float total_time);
 
-/* n back-to-back steps, total_time advancing by dt; if ms_out != NULL the whole batch is
- * timed with CUDA events on the context's stream and the call synchronises. */
+/* n back-to-back steps, total_time advancing by dt (float additions, exactly as n calls would); if ms_out != NULL the whole
+ * batch is timed with CUDA events on the context's stream and the call synchronises.  Same results as n calls of rvh_step,
+ * bit for bit; small scenes take a faster route to them: without the grid up to 32 steps ride in ONE kernel launch (the strands
+ * never interact), with the grid and no wind the step is captured once as a CUDA graph and replayed (nothing in its kernel
+ * parameters depends on time).  Per-kernel profiling (rvh_profile_enable) and RVH_NO_FAST_STEP_N=1 select plain stepping. */
 int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out);
 
 /* Host round trip in one call: upload Strand[S], one step, download Strand[S].  Only curvePoints and
  * curveVels cross PCIe (correctionVecs are dead on input; on output they are written only with
- * RVH_KEEP_CORRECTION, otherwise that third of the host buffer is left untouched). */
+ * RVH_KEEP_CORRECTION, otherwise that third of the host buffer is left untouched).
+ * From 128K strands up (and without RVH_KEEP_CORRECTION / imported buffers) the call is pipelined over 16 strand chunks on three
+ * streams: the upload of chunk c+1 runs beside the kernels of chunk c, and the POSITIONS of chunk c travel back while later
+ * chunks are still arriving (the gather changes velocities only); the velocities follow once the grid is complete.  Same
+ * bytes in the host buffer as upload + rvh_step + download.  Use pinned host memory, or the copies serialise. */
 int rvh_step_host(rvh_ctx* ctx, void* strands_inout, size_t bytes, float dt, float total_time);
 
 /* Read-backs (synchronise).  The reference never reads these back; tests do. */

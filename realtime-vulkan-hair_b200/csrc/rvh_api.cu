@@ -578,7 +578,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
 
 extern "C" {
 
-int rvh_abi_version(void) { return 2; }   // 2: rvh_config.repulsion, head SDF entry points
+int rvh_abi_version(void) { return 3; }   // 2: rvh_config.repulsion, head SDF entry points; 3: indirect / semaphore imports, debug hooks
 
 void rvh_default_config(rvh_config* cfg, int num_strands, int num_points) {
     std::memset(cfg, 0, sizeof *cfg);

@@ -12,16 +12,17 @@
 // accumulation makes the result independent of atomics order and of the GPU count.
 //
 // Kernels per step (grid on):
-//   k_ftl_step<V,WIND,NELL,GATHER>  [grid clear in the prologue on wide launches;] gather + friction (+ repulsion) of the PREVIOUS
+//   k_ftl_step<V,WIND,NELL,GATHER,MULTI>  [grid clear in the prologue on wide launches;] gather + friction (+ repulsion) of the PREVIOUS
 //                                   step's grid fused into the load (GATHER), collider tests (unrolled ellipsoids, optionally
 //                                   behind the collider candidate mask, or the head SDF by plain loads / TMA-staged tiles),
-//                                   then integrate + FTL + corrected velocity
+//                                   then integrate + FTL + corrected velocity.  MULTI (grid off): up to 32 whole steps per launch
 //   k_grid_splat<MAGIC>             two-phase register-accumulating integer splat, one RED.64 per lane and cell
-//   k_grid_exchange                 sharded runs: pull-reduce + finalize + push over NVLink peer memory (or ncclAllReduce)
+//   k_grid_exchange                 sharded runs: pull-reduce + finalize + push over NVLink peer memory (or ncclAllReduce); bounded waits
 //   k_grid_finalize                 int64 accumulators -> float4 cells (v/density, density) for the gather
 //   k_grid_gather<REP>              stand-alone gather, only when state is read back before the next step
-// Around the step: k_unpack_aos / k_pack_aos (Strand[S] AoS <-> planes), k_morton_keys, k_synth_head_aos,
-// k_mesh_follicles_aos (GPU scene init), k_sdf_bake_colliders / k_sdf_bake_mesh, k_expand_strands (hair.tesc/tese).
+// Around the step: k_unpack_aos / k_pack_aos (Strand[S] AoS <-> planes, by tile ranges for the pipelined host round trip),
+// k_write_indirect (imported draw arguments), k_morton_keys, k_synth_head_aos, k_mesh_follicles_aos (GPU scene init),
+// k_sdf_bake_colliders / k_sdf_bake_mesh, k_expand_strands (hair.tesc/tese), k_hit_masks (test hook: collider decisions).
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda.h>            // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(rvh.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.rvh_abi_version() == 2
+    assert L.rvh_abi_version() == 3
 
 
 def test_struct_sizes_match_reference_layouts():
