@@ -119,7 +119,7 @@ def _c_abi_smoke(tmp_path):
     subprocess.check_call([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_smoke.c"),
                            "-L", libdir, "-lrvh", "-Wl,-rpath," + libdir, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
-    assert "abi 2" in out.stdout and "config 76 bytes" in out.stdout
+    assert "abi 3" in out.stdout and "config 76 bytes" in out.stdout
     if _has_gpu():
         assert out.returncode == 0 and "10 steps ok" in out.stdout and "{900,1,0,0}" in out.stdout, out.stdout
     else:
