@@ -61,7 +61,6 @@ struct rvh_ctx {
     float* corr = nullptr;                // [3][N][S_pad] (RVH_KEEP_CORRECTION)
     unsigned long long* grid = nullptr;   // [G^3][4] int64 accumulators
     float4* fgrid = nullptr;              // [G^3] float cells for the gather (k_grid_finalize)
-    int k1_carveout = -1;                 // RVH_K1_CARVEOUT env (experiment): preferred shared-memory carve-out in percent, -1 = driver default
     int k1_blocks = 0, k1_launch_blocks = 0;   // CTAs of k_ftl_step for all strands / of the launch being issued (chunked launches)
     uint4* k1_clear = nullptr; unsigned k1_clear_n = 0;    // grid clear fused into k_ftl_step (set per step)
     size_t grid_bytes = 0;
@@ -204,13 +203,7 @@ void launch_k1(rvh_ctx* c, int gather) {
     // gather: 0 = none pending, 1 = friction, 2 = friction + repulsion (extension: V <= 2 only, see create_impl)
     if (gather == 2) {
         if constexpr (V <= 2) k_ftl_step<V, WIND, NELL, 2><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
-    } else if (gather == 1) {
-        if (c->k1_carveout >= 0) {       // experiment: L1 / shared split of the kernel with the fused gather (it uses no shared memory)
-            static bool done = false;
-            if (!done) { cudaFuncSetAttribute(k_ftl_step<V, WIND, NELL, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, c->k1_carveout); done = true; }
-        }
-        k_ftl_step<V, WIND, NELL, 1><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
-    }
+    } else if (gather == 1) k_ftl_step<V, WIND, NELL, 1><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
     else if constexpr (NELL < 100) k_ftl_step<V, WIND, NELL, 0><<<c->k1_launch_blocks, kBlock, 0, c->stream>>>(c->P, c->planes, c->corr, c->fgrid, c->sdf_map, c->k1_clear, c->k1_clear_n);
 }
 template <int V>
@@ -511,7 +504,6 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->S = cfg->num_strands; c->N = cfg->num_points;
     c->S_pad = ((c->S + kTileStrands - 1) / kTileStrands) * kTileStrands;
     c->rank = rank; c->nranks = nranks;
-    if (const char* e = std::getenv("RVH_K1_CARVEOUT")) c->k1_carveout = std::atoi(e);
     if (const char* e = std::getenv("RVH_SPLAT_WARPS")) c->splat_target_warps = std::max(1, std::atoi(e));
     int V = cfg->strands_per_thread;
     if (V == 4) V = 2;                                             // round 1 shipped a 4-strand kernel: it spilled (79-106 local ops) and never won; the value is still accepted

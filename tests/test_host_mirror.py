@@ -99,3 +99,37 @@ def test_mirror_single_frame_matches_c_abi_path(golden_c1, obj_path):
     direct = sim.download()
     sim.close()
     assert np.array_equal(bits(out), bits(direct))
+
+
+def test_mirror_keeps_the_reference_class_surface(tmp_path):
+    """The signatures SURVEY.md section 8(b) lists as staying intact (Strand.h:74-78, Scene.h:83-104, Renderer.h:14,66) must exist
+    in the mirror with the reference's argument lists: a translation unit written like the reference's main.cpp (main.cpp:226-283)
+    has to compile against rvh_host.hpp."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    src = tmp_path / "surface.cpp"
+    src.write_text(r'''
+#include "rvh_host.hpp"
+using namespace rvh_host;
+int use(Device* device, VkCommandPool pool, SwapChain* swapChain, Camera* camera, Camera* shadowCamera, std::vector<Model*> models) {
+    Hair* hair = new Hair(device, pool, "models/mannequin_segment.obj");
+    VkBuffer a = hair->GetStrandsBuffer(), b = hair->GetNumStrandsBuffer(), c = hair->GetModelBuffer();
+    int n = hair->GetNumStrands();
+    std::vector<Collider> colliders = { Collider(vec3{2.0f, 0.0f, 1.0f}, vec3{0.0f, 0.0f, 0.0f}, vec3{1.0f, 1.0f, 1.0f}) };
+    Scene* scene = new Scene(device, pool, colliders, models);
+    scene->AddHair(hair); scene->AddCollider(colliders[0]); scene->AddModel(nullptr);
+    const std::vector<Model*>& m = scene->GetModels(); const std::vector<Hair*>& h = scene->GetHair();
+    const std::vector<Collider>& cl = scene->GetColliders(); const std::vector<GridCell>& g = scene->GetGrid();
+    VkBuffer t = scene->GetTimeBuffer(), cb = scene->GetCollidersBuffer(), gb = scene->GetGridBuffer(), mb = scene->GetModelBuffer();
+    scene->UpdateTime(); scene->translateSphere(vec3{0.1f, 0.0f, 0.0f});
+    Renderer* renderer = new Renderer(device, swapChain, scene, camera, shadowCamera);
+    renderer->Frame();
+    hair->SetExportedStrandsMemory(a, -1, 0); hair->SetExportedIndirectMemory(b, -1, 0); hair->SetExportedSemaphore(-1);
+    return n + (int)m.size() + (int)h.size() + (int)cl.size() + (int)g.size() + (t == cb) + (gb == mb) + (c == a);
+}
+''')
+    inc = os.path.join(ROOT, "realtime-vulkan-hair_b200", "host")
+    subprocess.check_call([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", inc, str(src)])
