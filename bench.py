@@ -161,6 +161,25 @@ def _ref_tag(N, flags_s):
     return tag if orc.ref_available(tag) else None
 
 
+def vulkan_probe():
+    """BASELINE.json's intended CPU baseline is the unmodified compute.comp on Mesa lavapipe.  Probed at every start of the
+    reference arm: an ICD manifest, a Vulkan loader and a GLSL compiler are all needed to run it."""
+    import ctypes.util
+    import glob
+    import shutil
+    icds = [f for d in ("/usr/share/vulkan/icd.d", "/etc/vulkan/icd.d", os.path.expanduser("~/.local/share/vulkan/icd.d")) for f in glob.glob(os.path.join(d, "*.json"))]
+    icds += [f for f in os.environ.get("VK_ICD_FILENAMES", "").split(":") if f and os.path.exists(f)]
+    loader = ctypes.util.find_library("vulkan")
+    compiler = shutil.which("glslangValidator") or shutil.which("glslc")
+    lavapipe = [f for f in icds if "lvp" in os.path.basename(f) or "lavapipe" in os.path.basename(f)]
+    ok = bool(lavapipe and loader and compiler)
+    return {"available": ok, "icd_manifests": icds, "loader": loader, "glsl_compiler": compiler,
+            "note": "lavapipe + loader + GLSL compiler present: the shader could run through Vulkan, but no harness for it ships here" if ok else
+                    "compute.comp on Mesa lavapipe (BASELINE.json's intended CPU baseline) cannot run in this image: %s; the reference's shader text is compiled "
+                    "as C++ against its vendored glm instead (oracle/_ref)" % ", ".join(
+                        m for m, missing in (("no lavapipe ICD manifest", not lavapipe), ("no libvulkan", not loader), ("no glslangValidator/glslc", not compiler)) if missing)}
+
+
 _HOOK_T = C.CFUNCTYPE(None, C.c_int, C.c_void_p, C.c_size_t)
 
 
@@ -321,7 +340,7 @@ def run_reference(args):
            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * el / steps,
            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": cfg,
-           "cpu_baseline": dict(info, value=val, unit=UNIT),
+           "cpu_baseline": dict(info, value=val, unit=UNIT, lavapipe=vulkan_probe()),
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
