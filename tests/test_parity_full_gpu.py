@@ -272,3 +272,57 @@ def test_resident_steps_after_a_pipelined_host_step_run_on_morton_order_again():
     b.close()
     assert np.array_equal(bits(fa[:, 0:2]), bits(fb[:, 0:2]))
     assert ms_a <= 1.5 * ms_b + 0.05, "resident steps after rvh_step_host are slow: %.3f ms vs %.3f ms" % (ms_a, ms_b)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 33, 65])
+def test_step_n_batch_edges_with_correction_vectors(n):
+    """Batch boundaries of the many-steps launch (32 per launch) and correctionVecs (written by every step, RVH_KEEP_CORRECTION)."""
+    S, N = 2000, 12
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, 2.5, colliders=cols)
+    flags = rvh.WIND_B | rvh.KEEP_CORRECTION
+    a, b = _fresh(S, N, 2.5, flags, st, cols), _fresh(S, N, 2.5, flags, st, cols)
+    a.step_n(n, DT, 0.5)
+    t = np.float32(0.5)
+    for k in range(n):
+        b.step(DT, float(t))
+        t = np.float32(t + np.float32(DT))
+    fa, fb = a.download(), b.download()
+    a.close(); b.close()
+    assert np.array_equal(bits(fa), bits(fb))
+    assert np.abs(fa[:, 2, 1:, :3]).max() > 0
+
+
+@pytest.mark.parametrize("flags", [rvh.GRID_ON | rvh.REPULSION_ON, rvh.GRID_ON | rvh.KEEP_CORRECTION, rvh.GRID_ON | rvh.GRID_INT32_WRAP])
+def test_graph_replay_with_extension_and_layout_flags(flags):
+    S, N = 6000, 16
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, 2.5, colliders=cols)
+    a, b = _fresh(S, N, 2.5, flags, st, cols), _fresh(S, N, 2.5, flags, st, cols)
+    a.step_n(9, DT, 0.0)
+    for k in range(9):
+        b.step(DT, 0.0)
+    fa, fb, ga, gb = a.download(), b.download(), a.download_grid(), b.download_grid()
+    a.close(); b.close()
+    assert np.array_equal(bits(fa), bits(fb)) and np.array_equal(ga, gb)
+
+
+def test_pipelined_step_host_uneven_chunks_and_extensions(monkeypatch):
+    """Three uneven chunks (RVH_HOST_CHUNKS) with the head SDF and repulsion on: same bytes as upload + step + download."""
+    monkeypatch.setenv("RVH_HOST_CHUNKS", "3")
+    S, N, L = 131072 + 300, 8, 2.5
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, L, colliders=cols)
+    flags = rvh.GRID_ON | rvh.SDF_ON | rvh.REPULSION_ON | rvh.WIND_A
+    dim, origin, cell = [41, 63, 35], np.array([-2.0, -2.2, -1.8], np.float32), 0.1
+    rest = float(np.float32(L) / np.float32(N - 1))
+    ref_sim = rvh.HairSim(rvh.default_config(S, N, flags=flags, rest_length=rest))
+    ref_sim.set_colliders(cols); ref_sim.bake_head_sdf_from_colliders(dim, origin, cell)
+    ref_sim.upload(st); ref_sim.step(DT, 0.2)
+    ref = ref_sim.download(); ref_sim.close()
+    sim = rvh.HairSim(rvh.default_config(S, N, flags=flags, rest_length=rest))
+    sim.set_colliders(cols); sim.bake_head_sdf_from_colliders(dim, origin, cell)
+    buf = st.copy()
+    sim.step_host(buf, DT, 0.2)
+    sim.close()
+    assert np.array_equal(bits(buf[:, 0:2]), bits(ref[:, 0:2]))
