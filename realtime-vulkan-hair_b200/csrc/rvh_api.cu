@@ -108,6 +108,7 @@ struct rvh_ctx {
     unsigned* xflags = nullptr;           // [2][kMaxRanks] epochs + block counter, zero-initialised
     void* ipc_open[3 * kMaxRanks] = {};   // mappings to close
     unsigned epoch = 0;
+    int num_sms = 148;
     long long exchange_timeout_cycles = 0;   // RVH_EXCHANGE_TIMEOUT_MS (default 5000) in SM clocks: bound of every wait on a peer in k_grid_exchange
     bool grid_reduced = true;             // the int64 accumulators hold the all-rank sum (NCCL path, or 1 rank)
     // timing
@@ -330,7 +331,9 @@ int finalize_grid(rvh_ctx* ctx) {
         prof_begin(ctx, EV_AR);
         ctx->epoch += 1;
         const int per = (cells + ctx->nranks - 1) / ctx->nranks;
-        k_grid_exchange<<<std::min((per + 255) / 256, 148), 256, 0, ctx->stream>>>(ctx->peers, ctx->rank, ctx->nranks, cells, ctx->P.int32_wrap, ctx->epoch, ctx->exchange_timeout_cycles);
+        // one cell per thread when the slice allows it (all blocks co-resident: <= 4 per SM): every thread then pays ONE NVLink round trip,
+        // not one per loop iteration (2 ranks: 131,072 cells per slice used to take 3-4 trips through 148 blocks)
+        k_grid_exchange<<<std::min((per + 255) / 256, 4 * ctx->num_sms), 256, 0, ctx->stream>>>(ctx->peers, ctx->rank, ctx->nranks, cells, ctx->P.int32_wrap, ctx->epoch, ctx->exchange_timeout_cycles);
         prof_end(ctx);
     } else {
         prof_begin(ctx, EV_FINALIZE);
@@ -530,6 +533,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->aos_bytes = (size_t)c->S * 48 * c->N;
     CUC(cudaMalloc(&c->aos_dev, c->aos_bytes));
     CUC(cudaEventCreate(&c->ev_a)); CUC(cudaEventCreate(&c->ev_b));
+    CUC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
 
     StepParams& P = c->P;
     std::memset(&P, 0, sizeof P);
