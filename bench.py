@@ -359,12 +359,39 @@ class Ranks:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
         torch.cuda.set_device(self.local)
+        self.numa = self._bind_to_gpu_numa_node() if self.world > 1 else "1 GPU: not bound"
         self.dist = None
         self.rvh = rvh
         if self.world > 1:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.dist = dist
+
+    def _bind_to_gpu_numa_node(self):
+        """Multi-GPU e2e is host-bound: every rank streams 2 x 50 GB/s through pinned host memory.  Run each rank (and so allocate its
+        pinned buffers) on the NUMA node its GPU hangs off, so that the copies do not cross the socket interconnect."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.local]) if vis and vis.split(",")[0].isdigit() else self.local
+            bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            bdf = bus.lower()[-12:]                                   # 00000000:1B:00.0 -> 0000:1b:00.0
+            node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+            if node < 0:
+                return "GPU %s reports no NUMA node: not bound" % bdf
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if not cpus:
+                return "NUMA node %d of GPU %s has no CPU this process may use: not bound" % (node, bdf)
+            os.sched_setaffinity(0, cpus)
+            return "rank %d bound to NUMA node %d (%d CPUs) of GPU %s" % (self.rank, node, len(cpus), bdf)
+        except Exception as e:                                        # no NVML / no sysfs: run unbound
+            return "not bound (%s)" % type(e).__name__
 
     def new_nccl_id(self):
         """A fresh ncclUniqueId from rank 0 (one per sharded context)."""
@@ -571,7 +598,7 @@ def measure(R, rvh, args, workload, steps, warmup, scaling, full):
     out = {"workload": workload, "value": value, "ms_per_step": ms / steps, "steps": steps, "roofline": roofline, "gpu_launches": int(launches),
            "clocks": clocks, "S": S, "S_total": S_total, "N": N, "flags_s": flags_s, "cols_nbytes": int(cols.nbytes),
            "implementation": {"scene_init": "reference scene frozen from Hair::Hair (tests/golden/c1_reference_scene.npz) + upload" if c1 else ("GPU (rvh_init_synthetic_head)" if device_init else "host (scenes.synthetic_head) + upload"),
-                              "parallelism": "strand-sharded x%d, grid exchange per step: %s" % (R.world, exchange) if R.world > 1 else "1 GPU",
+                              "parallelism": "strand-sharded x%d, grid exchange per step: %s" % (R.world, exchange) if R.world > 1 else "1 GPU", "numa": R.numa,
                               "strands_per_thread": int(sim.cfg.strands_per_thread),
                               "step_n_fast_path": fast or "none",
                               "head_sdf": ("%s lattice, cell %.3f, sampled through %s" % ("x".join(str(d) for d in sdf_lattice()[0]), SDF_CELL, sdf_mode)) if flags & rvh.SDF_ON else None}}
