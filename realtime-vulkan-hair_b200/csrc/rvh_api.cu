@@ -78,6 +78,9 @@ struct rvh_ctx {
     unsigned* sort_keys = nullptr; unsigned* sort_keys_out = nullptr; int* sort_ids = nullptr;
     StepParams P;
     bool uploaded = false, colliders_set = false;
+    unsigned long long* scene_timing = nullptr;                        // RVH_SCENE_TIMING=1: phase time stamps of CTA 0, printed after every launch (tuning)
+    unsigned* scene_bar = nullptr; unsigned scene_bar_base = 0u;       // k_scene_step's grid barrier: monotonic device counter, its value before the next launch
+    int scene_ctas_per_sm = 2;            // RVH_SCENE_CTAS env (tuning; 0 = off): CTAs per SM of the persistent small-scene kernel k_scene_step
     int splat_target_warps = 32768;       // RVH_SPLAT_WARPS env (tuning): the splat splits rows over blockIdx.y until it has this many warps
     // rvh_step_n fast paths for small scenes: several steps per launch (grid off), CUDA-graph replay of the step (grid on, wind off)
     cudaGraphExec_t step_graph = nullptr; float step_graph_dt = 0.f; unsigned step_graph_version = 0, state_version = 1; int step_graph_launches = 0;
@@ -323,6 +326,90 @@ int launch_multi_step(rvh_ctx* ctx, int n, float dt, float& t) {      // t advan
     return RVH_OK;
 }
 
+// Small scene, grid on, gather pending: `n` steps (<= 32) in ONE cooperative launch of k_scene_step (see the kernel).
+bool scene_step_eligible(const rvh_ctx* ctx) {
+    const int flags = ctx->cfg.flags;
+    return ctx->scene_ctas_per_sm > 0 && (flags & RVH_GRID_ON) && !(flags & (RVH_SDF_ON | RVH_REPULSION_ON)) && ctx->nranks == 1 &&
+           ctx->uploaded && ctx->colliders_set && !ctx->needs_resort && ctx->profiling == 0 &&
+           !ctx->interop_aos && !ctx->interop_indirect && !ctx->interop_sem &&
+           ctx->V <= 2 && ctx->k1_blocks * 2 <= ctx->num_sms && ctx->P.scale > 0.f && ctx->P.scale < 8388608.0f;
+}
+
+template <int V, bool WIND, int NELL>
+int launch_scene_kernel(rvh_ctx* ctx, int n, int blocks, int splat_bx, int splat_items, int rpc) {
+    void* fn = (void*)k_scene_step<V, WIND, NELL>;
+    if (blocks == 0) {                                                  // query: co-resident CTAs per SM
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scene_step<V, WIND, NELL>, kBlock, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return per_sm;
+    }
+    int k1 = ctx->k1_blocks;
+    void* args[] = { (void*)&ctx->P, (void*)&ctx->planes, (void*)&ctx->corr, (void*)&ctx->grid, (void*)&n, (void*)&k1,
+                     (void*)&splat_bx, (void*)&splat_items, (void*)&rpc, (void*)&ctx->scene_bar, (void*)&ctx->scene_bar_base, (void*)&ctx->scene_timing };
+    return (int)cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kBlock), args, 0, ctx->stream);
+}
+
+int scene_kernel_dispatch(rvh_ctx* ctx, bool wind, int n, int blocks, int splat_bx, int splat_items, int rpc) {
+    const bool five = ctx->P.n_ell == 5;
+#define RVH_SCENE(V_, W_, NE_) launch_scene_kernel<V_, W_, NE_>(ctx, n, blocks, splat_bx, splat_items, rpc)
+    if (ctx->V == 2) {
+        if (five) return wind ? RVH_SCENE(2, true, 5) : RVH_SCENE(2, false, 5);
+        return wind ? RVH_SCENE(2, true, -1) : RVH_SCENE(2, false, -1);
+    }
+    if (five) return wind ? RVH_SCENE(1, true, 5) : RVH_SCENE(1, false, 5);
+    return wind ? RVH_SCENE(1, true, -1) : RVH_SCENE(1, false, -1);
+#undef RVH_SCENE
+}
+
+int launch_scene_steps(rvh_ctx* ctx, int n, float dt, float& t) {      // t advances exactly as n calls of rvh_step would move it
+    { int r = flush_gather(ctx); if (r) return r; }                     // an ordinary step left its gather to its successor: apply it now
+    StepParams& P = ctx->P;
+    const int flags = ctx->cfg.flags;
+    const bool wind = flags & (RVH_WIND_A | RVH_WIND_B);
+    P.dt = dt; P.inv_dt = 1.0f / dt; P.dt2 = dt * dt; P.vel_scale = P.damping / dt;
+    P.wind_mode = (flags & RVH_WIND_B) ? 2 : ((flags & RVH_WIND_A) ? 1 : 0);
+    for (int k = 0; k < n; ++k, t += dt) {
+        float s2T = 0.f, T3 = 0.f, amp = 0.f;
+        if (wind) wind_scalars(P.wind_mode, t, s2T, T3, amp);
+        P.wind_tab[3 * k] = amp * s2T; P.wind_tab[3 * k + 1] = T3; P.wind_tab[3 * k + 2] = amp;
+    }
+    P.cta0 = 0; P.strand0 = 0;
+    const int per_sm = std::min(ctx->scene_ctas_per_sm, scene_kernel_dispatch(ctx, wind, n, 0, 0, 0, 0));
+    if (per_sm < 1) return fail(ctx, RVH_ERR_CUDA, "k_scene_step does not fit on an SM");
+    const int max_blocks = per_sm * ctx->num_sms;
+    // The launch is sized to the scene, not to the machine: every barrier costs one atomic per CTA.  Enough CTAs for the FTL chains plus
+    // a clearing crew beside them, for one splat item (128 strands x a chunk of rows) per CTA, and for one gather pack per thread.
+    const int splat_bx = ctx->S_pad / kSplatThreads, rows = ctx->N - 1;
+    const int points = rows * ctx->S_pad;
+    int blocks = std::max(ctx->k1_blocks + std::max(16, ctx->k1_blocks), (points + kBlock - 1) / kBlock);
+    blocks = std::max(blocks, std::min(splat_bx * rows, 2 * ctx->num_sms));
+    blocks = std::min(blocks, max_blocks);
+    int chunks = std::max(1, std::min(rows, (blocks + splat_bx - 1) / splat_bx));
+    const int rpc = (rows + chunks - 1) / chunks;
+    chunks = (rows + rpc - 1) / rpc;
+    if (!ctx->scene_timing && std::getenv("RVH_SCENE_TIMING")) CU(cudaMalloc(&ctx->scene_timing, (1 + 6 * 32) * sizeof(unsigned long long)));
+    if (!ctx->scene_bar) {
+        CU(cudaMalloc(&ctx->scene_bar, sizeof(unsigned)));
+        CU(cudaMemsetAsync(ctx->scene_bar, 0, sizeof(unsigned), ctx->stream));
+        ctx->scene_bar_base = 0u;
+    }
+    const int e = scene_kernel_dispatch(ctx, wind, n, blocks, splat_bx, splat_bx * chunks, rpc);
+    if (e != 0) { cudaGetLastError(); return fail(ctx, RVH_ERR_CUDA, std::string("cudaLaunchCooperativeKernel(k_scene_step): ") + cudaGetErrorString((cudaError_t)e)); }
+    ctx->scene_bar_base += 3u * (unsigned)n * (unsigned)blocks;         // the counter is monotonic (compared modulo 2^32)
+    if (ctx->scene_timing) {                                            // tuning aid: mean duration of every phase and barrier over the launch's steps
+        std::vector<unsigned long long> ts(1 + 6 * (size_t)n);
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(ts.data(), ctx->scene_timing, ts.size() * sizeof(ts[0]), cudaMemcpyDeviceToHost));
+        double acc[6] = { 0, 0, 0, 0, 0, 0 };
+        for (int k = 0; k < n; ++k) for (int j = 0; j < 6; ++j) acc[j] += (double)(ts[1 + 6 * k + j] - ts[6 * k + j]);
+        std::fprintf(stderr, "[k_scene_step] %d CTAs, %d steps, CTA 0 mean ns: ftl|clear %.0f  barrier %.0f  splat %.0f  barrier %.0f  gather %.0f  barrier %.0f  = %.0f per step\n",
+                     blocks, n, acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, (double)(ts[6 * (size_t)n] - ts[0]) / n);
+    }
+    ctx->launches += 1;
+    ctx->gather_pending = false;                                        // applied inside the launch; the float grid was not produced
+    return RVH_OK;
+}
+
 // The step's grid is complete on this rank: make the float grid the gather reads (compute.comp:276-286), summed over the ranks.
 int finalize_grid(rvh_ctx* ctx) {
     const int cells = ctx->P.G * ctx->P.G * ctx->P.G;
@@ -507,6 +594,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->S = cfg->num_strands; c->N = cfg->num_points;
     c->S_pad = ((c->S + kTileStrands - 1) / kTileStrands) * kTileStrands;
     c->rank = rank; c->nranks = nranks;
+    if (const char* e = std::getenv("RVH_SCENE_CTAS")) c->scene_ctas_per_sm = std::max(0, std::min(4, std::atoi(e)));
     if (const char* e = std::getenv("RVH_SPLAT_WARPS")) c->splat_target_warps = std::max(1, std::atoi(e));
     int V = cfg->strands_per_thread;
     if (V == 4) V = 2;                                             // round 1 shipped a 4-strand kernel: it spilled (79-106 local ops) and never won; the value is still accepted
@@ -563,6 +651,10 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
         P.splat_vagg = v;
     }
     P.keep_corr = c->corr ? 1 : 0;
+    // sparse hair: below ~64K strands a warp's 32 Morton neighbours stop sharing cells (RVH_SPLAT_SPARSE: the distinct-cell count
+    // from which a row is splatted point by point; 0 = never)
+    P.splat_sparse = c->S < 65536 ? 5 : 0;
+    if (const char* e = std::getenv("RVH_SPLAT_SPARSE")) P.splat_sparse = std::max(0, std::atoi(e));
 
     if (nranks > 1) {
         std::string err;
@@ -1035,6 +1127,10 @@ int rvh_debug_set_interop_device_buffers(rvh_ctx* ctx, void* strands_dev, size_t
 int rvh_step(rvh_ctx* ctx, float dt, float total_time) {
     if (!ctx) return RVH_ERR_INVALID;
     CU(cudaSetDevice(ctx->cfg.device));
+    if (dt > 0.f && scene_step_eligible(ctx) && !std::getenv("RVH_NO_FAST_STEP_N")) {   // small scene in its steady state: one launch per step
+        float t = total_time;
+        return launch_scene_steps(ctx, 1, dt, t);
+    }
     return do_step(ctx, dt, total_time, 3, true);
 }
 
@@ -1060,6 +1156,20 @@ int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out) 
         while (done < n) {
             const int m = std::min(32, n - done);
             int r = launch_multi_step(ctx, m, dt, t);
+            if (r) return r;
+            done += m;
+        }
+    } else if (plain && grid && n >= 2 && ctx->scene_ctas_per_sm > 0 && ctx->k1_blocks * 2 <= ctx->num_sms && !(flags & RVH_REPULSION_ON) &&
+               !ctx->interop_indirect && !ctx->interop_sem) {
+        // small scene with the grid on: whole steps (up to 32 of them) inside ONE persistent cooperative launch (k_scene_step)
+        if (!scene_step_eligible(ctx)) {                               // a pipelined host step left the caller's strand order: one ordinary step restores the Morton order
+            int r = do_step(ctx, dt, t, 3, true);
+            if (r) return r;
+            done = 1; t += dt;
+        }
+        while (done < n && scene_step_eligible(ctx)) {
+            const int m = std::min(32, n - done);
+            int r = launch_scene_steps(ctx, m, dt, t);
             if (r) return r;
             done += m;
         }
@@ -1275,6 +1385,7 @@ void rvh_destroy(rvh_ctx* c) {
     if (c->interop_sem) cudaDestroyExternalSemaphore(c->interop_sem);
     cudaFree(c->cmask_dev);
     cudaFree(c->sdf_dev); cudaFree(c->bake_tris); cudaFree(c->exp_tab); cudaFree(c->exp_pw); cudaFree(c->exp_tu);
+    cudaFree(c->scene_bar); cudaFree(c->scene_timing);
     cudaFree(c->planes); cudaFree(c->corr); cudaFree(c->grid); cudaFree(c->fgrid); cudaFree(c->perm); cudaFree(c->aos_dev);
     cudaFree(c->sort_tmp); cudaFree(c->sort_keys); cudaFree(c->sort_keys_out); cudaFree(c->sort_ids);
     if (c->step_graph) cudaGraphExecDestroy(c->step_graph);

@@ -16,7 +16,9 @@
 //                                   step's grid fused into the load (GATHER), collider tests (unrolled ellipsoids, optionally
 //                                   behind the collider candidate mask, or the head SDF by plain loads / TMA-staged tiles),
 //                                   then integrate + FTL + corrected velocity.  MULTI (grid off): up to 32 whole steps per launch
-//   k_grid_splat<MAGIC>             two-phase register-accumulating integer splat, one RED.64 per lane and cell
+//   k_grid_splat<MAGIC>             two-phase register-accumulating integer splat, one RED.64 per lane and cell (sparse rows: point by point)
+//   k_scene_step<V,WIND,NELL>       small scenes: whole steps in ONE persistent cooperative launch (FTL || clear | splat | per-point gather
+//                                   from the raw accumulators, grid-wide barriers in between); rvh_step / rvh_step_n use it
 //   k_grid_exchange                 sharded runs: pull-reduce + finalize + push over NVLink peer memory (or ncclAllReduce); bounded waits
 //   k_grid_finalize                 int64 accumulators -> float4 cells (v/density, density) for the gather
 //   k_grid_gather<REP>              stand-alone gather, only when state is read back before the next step
@@ -76,6 +78,7 @@ struct StepParams {
     int cta0, strand0;                      // chunked launches (rvh_step_host's pipeline): first CTA of this k_ftl_step launch, first strand of this splat launch
     int multi_steps;                        // k_ftl_step<..., MULTI>: steps per launch (grid off: strands are independent); wind_tab = per-step (amp*s2T, T3, amp)
     float wind_tab[3 * 32];
+    int splat_sparse;                       // k_grid_splat: rows whose 32 points fall into at least this many distinct base cells go to the grid point by point (0 = never)
     float splat_vagg;                       // k_grid_splat: points with |v|_inf <= splat_vagg are aggregated in int32 registers (32 contributions of <= 2^26 each)
 };
 
@@ -231,7 +234,43 @@ __device__ __forceinline__ void splat_point_direct(const StepParams& P, unsigned
 // coarse (2x2x2-cell) box: bit j set <=> ellipsoid j can contain a point of that box (conservative).  `cand` returns the OR
 // over the pack (all ones when a point is outside the grid); the caller ORs it over the warp and k_ftl_step then runs only
 // the ellipsoid tests that can hit -- typically 1-2 of 5, each worth 12 FFMA2 and as many constant loads.
-template <class T, bool REP, bool CMASK = false>
+// COH: weak (coherent) ld.global instead of the non-coherent read-only path.  The persistent k_scene_step reads data that other
+// CTAs of the SAME launch wrote before a grid-wide barrier (float grid, planes): ld.global.nc / LDG.CONSTANT may return stale lines there.
+// cell = (float(vel) * (1 / float(density))) per component, zero where density <= 0 (compute.comp:276-286)
+__device__ __forceinline__ float4 finalize_cell(longlong2 v01, longlong2 v2d, int int32_wrap) {
+    long long dens = v2d.y, v0 = v01.x, v1 = v01.y, v2 = v2d.x;
+    if (int32_wrap) { dens = (int)dens; v0 = (int)v0; v1 = (int)v1; v2 = (int)v2; }   // the reference's int32 GridCell
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dens > 0) {
+        const float rd = __frcp_rn(__ll2float_rn(dens));                 // 1.0 / float(density), compute.comp:283
+        o.x = __ll2float_rn(v0) * rd; o.y = __ll2float_rn(v1) * rd; o.z = __ll2float_rn(v2) * rd; o.w = __ll2float_rn(dens);
+    }
+    return o;
+}
+
+// SRC 0: float grid through the read-only path; 1: float grid, coherent; 2: `fg` really is the int64 accumulator grid -- the cell
+// is converted on the fly exactly as k_grid_finalize would have (k_scene_step: no finalize phase, no float grid at all).
+template <int SRC> __device__ __forceinline__ float4 ld_cell(const float4* fg, int idx, int int32_wrap) {
+    if (SRC == 0) return __ldg(fg + idx);
+    if (SRC == 1) {
+        float4 v;
+        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(fg + idx));
+        return v;
+    }
+    const unsigned long long* c = reinterpret_cast<const unsigned long long*>(fg) + 4 * (size_t)idx;
+    longlong2 a, b;
+    asm volatile("ld.global.v2.s64 {%0, %1}, [%2];" : "=l"(a.x), "=l"(a.y) : "l"(c));
+    asm volatile("ld.global.v2.s64 {%0, %1}, [%2];" : "=l"(b.x), "=l"(b.y) : "l"(c + 2));
+    return finalize_cell(a, b, int32_wrap);
+}
+template <bool COH> __device__ __forceinline__ float ld_plane(const float* p) {
+    if (!COH) return __ldg(p);
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+template <class T, bool REP, bool CMASK = false, int SRC = 0>
 __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* __restrict__ fgrid, T px, T py, T pz, T& vx, T& vy, T& vz, unsigned& cand) {
     constexpr int n = VecTraits<T>::n;
     float rho[n], rgx[n], rgy[n], rgz[n];
@@ -255,9 +294,9 @@ __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* _
             cand |= __ldg(P.cmask + ((X.f[i] >> 1) + ((Y.f[i] >> 1) + (Z.f[i] >> 1) * P.cmask_dim) * P.cmask_dim));
     }
     if (interior) {                                                     // all 8 corners of every point are cells
-        const float4* base[n];
+        int base[n];
 #pragma unroll
-        for (int i = 0; i < n; ++i) base[i] = fgrid + (X.f[i] + (Y.f[i] + Z.f[i] * P.G) * P.G);
+        for (int i = 0; i < n; ++i) base[i] = X.f[i] + (Y.f[i] + Z.f[i] * P.G) * P.G;
         const int sy = P.G, sz = P.G * P.G;
 #pragma unroll
         for (int cz = 0; cz < 2; ++cz)
@@ -267,7 +306,7 @@ __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* _
                 const int off = (ab & 1) + (ab >> 1) * sy + cz * sz;
 #pragma unroll
                 for (int i = 0; i < n; ++i) {
-                    const float4 cell = __ldg(base[i] + off);
+                    const float4 cell = ld_cell<SRC>(fgrid, base[i] + off, P.int32_wrap);
                     const float w = el(tw, i);
                     gxy[i] = __ffma2_rn(make_float2(w, w), make_float2(cell.x, cell.y), gxy[i]);
                     gz[i] = fmaf(w, cell.z, gz[i]);
@@ -289,7 +328,7 @@ __device__ __forceinline__ void gather_pack(const StepParams& P, const float4* _
                 for (int ab = 0; ab < 4; ++ab) {
                     const int fx = X.f[i] + (ab & 1), fy = Y.f[i] + (ab >> 1), fz = Z.f[i] + cz;
                     if (!isnan_[i] && cell_ok(fx, P.G) && cell_ok(fy, P.G) && cell_ok(fz, P.G)) {
-                        const float4 cell = __ldg(fgrid + (fx + (fy + fz * P.G) * P.G));
+                        const float4 cell = ld_cell<SRC>(fgrid, fx + (fy + fz * P.G) * P.G, P.int32_wrap);
                         const float w = el(xy[ab], i) * el(cz ? Z.w1 : Z.w0, i);
                         gxy[i] = __ffma2_rn(make_float2(w, w), make_float2(cell.x, cell.y), gxy[i]);
                         gz[i] = fmaf(w, cell.z, gz[i]);
@@ -502,7 +541,7 @@ __device__ __forceinline__ void collision_force(const StepParams& P, const SdfTi
 // GATHER != 0: the previous step's gather (+ repulsion when 2) is applied to (vx,vy,vz) right before they are first used,
 // i.e. AFTER the collision tests, whose work hides the latency of the cells prefetched at the top.
 struct WindNow { float amp_s2T, T3, amp; };   // this step's time-only wind scalars (host-evaluated): wind_amp * 2 sin(2T), 3T mod 2 pi, wind_amp
-template <class T, bool WIND, int NELL, int GATHER>
+template <class T, bool WIND, int NELL, int GATHER, bool COH = false>
 __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const WindNow& W, const SdfTile& tile, const float4* __restrict__ fgrid,
                                                     T cx, T cy, T cz, T vx, T vy, T vz, T parx, T pary, T parz) {
     constexpr int n = VecTraits<T>::n;
@@ -512,7 +551,7 @@ __device__ __forceinline__ PointOut<T> point_update(const StepParams& P, const W
     unsigned cand = ~0u;                                                // ellipsoids that can hit a point of this warp's row
     if (GATHER && RVH_K1_PREFETCH) gather_prefetch<T>(P, fgrid, cx, cy, cz);
     if (GATHER && !RVH_K1_PREFETCH) {
-        gather_pack<T, GATHER == 2, CMASK>(P, fgrid, cx, cy, cz, vx, vy, vz, cand);
+        gather_pack<T, GATHER == 2, CMASK, COH ? 1 : 0>(P, fgrid, cx, cy, cz, vx, vy, vz, cand);
         if (CMASK) cand = __reduce_or_sync(0xffffffffu, cand);          // warp-uniform: the skipped tests cost no divergence
     }
     T fx = bc<T>(0.0f), fy = bc<T>(P.gravity_y), fz = bc<T>(0.0f);       // :150
@@ -701,53 +740,41 @@ __device__ __forceinline__ void sdf_stage_row(const StepParams& P, const CUtenso
     }
 }
 
-// MULTI (grid off only): P.multi_steps steps in ONE launch.  Without the grid the strands never interact, so a thread simply
-// walks its strands again (its own stores of step k are its loads of step k+1; the state of a small scene sits in L1/L2);
-// the time-only wind scalars of every step come from the host-built P.wind_tab.  A 16K x 32 scene is launch- and
-// latency-bound (3.8 us of HBM time per step): this removes the launch, rvh_step_n uses it.
-template <int V, bool WIND, int NELL, int GATHER, bool MULTI = false>
-__global__ void __launch_bounds__(kBlock, (NELL <= -2 || GATHER == 2) ? RVH_K1X_MINBLOCKS : (GATHER ? RVH_K1G_MINBLOCKS : RVH_K1_MINBLOCKS))
-k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr,
-           const float4* __restrict__ fgrid, const __grid_constant__ CUtensorMap sdf_map, uint4* __restrict__ grid_clear, unsigned grid_clear_n) {
+// One thread's strands, root -> tip, `nsteps` times.  MULTI: this step's wind scalars come from P.wind_tab[step0 + step]; COH: the
+// planes (and, in point_update, the float grid) are read by coherent loads -- the launch itself wrote them (MULTI / k_scene_step).
+template <int V, bool WIND, int NELL, int GATHER, bool MULTI, bool COH>
+__device__ __forceinline__ void ftl_walk(const StepParams& P, float* __restrict__ planes, float* __restrict__ corr, const float4* __restrict__ fgrid,
+                                         const CUtensorMap* sdf_map, SdfStageSmem& sm, int cta, int nsteps, int step0) {
     using T = typename PackOf<V>::T;
     constexpr int NP = PackOf<V>::n;
     constexpr bool TMA = NELL == -3;
-    static_assert(!MULTI || (GATHER == 0 && !TMA), "several steps per launch need independent strands: no grid, no staged tiles");
-    // The step's grid clear (Renderer.cpp:2063) rides here when the launch is wide enough: this kernel never touches the
-    // int64 accumulators (it reads the float grid), the splat that fills them comes after it in the stream, and whoever
-    // read them last (finalize / exchange / a download) came before it.  Saves the memset launch.
-    if (grid_clear)
-        for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < grid_clear_n; k += gridDim.x * blockDim.x) grid_clear[k] = make_uint4(0u, 0u, 0u, 0u);
-    __shared__ __align__(128) unsigned char sdf_raw[TMA ? sizeof(SdfStageSmem) : 16];
-    SdfStageSmem& sm = *reinterpret_cast<SdfStageSmem*>(sdf_raw);
-    const int t = (P.cta0 + blockIdx.x) * blockDim.x + threadIdx.x;
+    const int t = (P.cta0 + cta) * blockDim.x + threadIdx.x;
     const int s0 = t * V;
     if (!TMA && s0 >= P.S_pad) return;                            // TMA variant: S_pad is a multiple of kBlock*V (V <= 2), no partial CTA
     const size_t RS = (size_t)P.S_pad * 6;                      // elements per row (all tiles, six planes)
     constexpr int PK = kTileStrands;                              // plane stride inside a tile: compile-time offsets
     float* const base = planes + tiled_index(6, P.S_pad, 0, 0, s0);
 
-    const int nsteps = MULTI ? P.multi_steps : 1;
     for (int step = 0; step < nsteps; ++step) {
-    const WindNow W = MULTI ? WindNow{ P.wind_tab[3 * step], P.wind_tab[3 * step + 1], P.wind_tab[3 * step + 2] } : WindNow{ P.wind_amp * P.wind_s2T, P.wind_T3, P.wind_amp };
+    const WindNow W = MULTI ? WindNow{ P.wind_tab[3 * (step0 + step)], P.wind_tab[3 * (step0 + step) + 1], P.wind_tab[3 * (step0 + step) + 2] } : WindNow{ P.wind_amp * P.wind_s2T, P.wind_T3, P.wind_amp };
     T parx[NP], pary[NP], parz[NP];
-    load_packs<V, MULTI>(base, parx); load_packs<V, MULTI>(base + PK, pary); load_packs<V, MULTI>(base + 2 * PK, parz);
+    load_packs<V, COH>(base, parx); load_packs<V, COH>(base + PK, pary); load_packs<V, COH>(base + 2 * PK, parz);
     T nx[NP], ny[NP], nz[NP], nvx[NP], nvy[NP], nvz[NP];
     float* nextp = base + RS;                                     // row 1
-    load_packs<V, MULTI>(nextp, nx); load_packs<V, MULTI>(nextp + PK, ny); load_packs<V, MULTI>(nextp + 2 * PK, nz);
-    load_packs<V, MULTI>(nextp + 3 * PK, nvx); load_packs<V, MULTI>(nextp + 4 * PK, nvy); load_packs<V, MULTI>(nextp + 5 * PK, nvz);
+    load_packs<V, COH>(nextp, nx); load_packs<V, COH>(nextp + PK, ny); load_packs<V, COH>(nextp + 2 * PK, nz);
+    load_packs<V, COH>(nextp + 3 * PK, nvx); load_packs<V, COH>(nextp + 4 * PK, nvy); load_packs<V, COH>(nextp + 5 * PK, nvz);
     T n2x[NP], n2y[NP], n2z[NP];                                  // TMA only: positions two rows ahead
     unsigned phase = 0;                                           // TMA only: mbarrier phase bit per buffer
     int bx = 0, by = 0, bz = 0;                                   // TMA only: origin of the tile of the row being consumed
     const int wid = threadIdx.x >> 5;
     if constexpr (TMA) {
-        if (P.N > 2) { load_packs<V, MULTI>(nextp + RS, n2x); load_packs<V, MULTI>(nextp + RS + PK, n2y); load_packs<V, MULTI>(nextp + RS + 2 * PK, n2z); }
+        if (P.N > 2) { load_packs<V, COH>(nextp + RS, n2x); load_packs<V, COH>(nextp + RS + PK, n2y); load_packs<V, COH>(nextp + RS + 2 * PK, n2z); }
         if ((threadIdx.x & 31) == 0) {
             mbar_init(&sm.bar[wid][0], 1); mbar_init(&sm.bar[wid][1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        sdf_stage_row<T, NP>(P, &sdf_map, sm, 1, nx, ny, nz, bx, by, bz);
+        sdf_stage_row<T, NP>(P, sdf_map, sm, 1, nx, ny, nz, bx, by, bz);
     }
     T lvx[NP], lvy[NP], lvz[NP];   // clamped velocity of the previous point, correction pending
 #pragma unroll
@@ -765,26 +792,26 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
         SdfTile tile = { nullptr, 0, 0, 0 };
         if constexpr (!TMA) {
             if (i + 1 < P.N) {
-                load_packs<V, MULTI>(nextp, nx); load_packs<V, MULTI>(nextp + PK, ny); load_packs<V, MULTI>(nextp + 2 * PK, nz);
-                load_packs<V, MULTI>(nextp + 3 * PK, nvx); load_packs<V, MULTI>(nextp + 4 * PK, nvy); load_packs<V, MULTI>(nextp + 5 * PK, nvz);
+                load_packs<V, COH>(nextp, nx); load_packs<V, COH>(nextp + PK, ny); load_packs<V, COH>(nextp + 2 * PK, nz);
+                load_packs<V, COH>(nextp + 3 * PK, nvx); load_packs<V, COH>(nextp + 4 * PK, nvy); load_packs<V, COH>(nextp + 5 * PK, nvz);
             }
         } else {
             if (i + 1 < P.N) {
 #pragma unroll
                 for (int u = 0; u < NP; ++u) { nx[u] = n2x[u]; ny[u] = n2y[u]; nz[u] = n2z[u]; }
-                load_packs<V, MULTI>(nextp + 3 * PK, nvx); load_packs<V, MULTI>(nextp + 4 * PK, nvy); load_packs<V, MULTI>(nextp + 5 * PK, nvz);
-                if (i + 2 < P.N) { load_packs<V, MULTI>(nextp + RS, n2x); load_packs<V, MULTI>(nextp + RS + PK, n2y); load_packs<V, MULTI>(nextp + RS + 2 * PK, n2z); }
+                load_packs<V, COH>(nextp + 3 * PK, nvx); load_packs<V, COH>(nextp + 4 * PK, nvy); load_packs<V, COH>(nextp + 5 * PK, nvz);
+                if (i + 2 < P.N) { load_packs<V, COH>(nextp + RS, n2x); load_packs<V, COH>(nextp + RS + PK, n2y); load_packs<V, COH>(nextp + RS + 2 * PK, n2z); }
             }
             const int b = i & 1;
             tile.data = sm.tile[wid][b]; tile.ox = bx; tile.oy = by; tile.oz = bz;
-            if (i + 1 < P.N) sdf_stage_row<T, NP>(P, &sdf_map, sm, i + 1, nx, ny, nz, bx, by, bz);   // tile of row i+1 flies while row i is computed
+            if (i + 1 < P.N) sdf_stage_row<T, NP>(P, sdf_map, sm, i + 1, nx, ny, nz, bx, by, bz);   // tile of row i+1 flies while row i is computed
             mbar_wait(&sm.bar[wid][b], (phase >> b) & 1u);
             phase ^= 1u << b;
         }
         T fvx[NP], fvy[NP], fvz[NP], odx[NP], ody[NP], odz[NP];
 #pragma unroll
         for (int u = 0; u < NP; ++u) {
-            const PointOut<T> o = point_update<T, WIND, NELL, GATHER>(P, W, tile, fgrid, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
+            const PointOut<T> o = point_update<T, WIND, NELL, GATHER, COH>(P, W, tile, fgrid, cx[u], cy[u], cz[u], vx[u], vy[u], vz[u], parx[u], pary[u], parz[u]);
             parx[u] = o.px; pary[u] = o.py; parz[u] = o.pz;
             odx[u] = o.dx; ody[u] = o.dy; odz[u] = o.dz;
             // finalise point i-1: v_{i-1} -= d_i / dt   (compute.comp:213-215)
@@ -802,6 +829,26 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
     // last point: no correction term (compute.comp:213 `i != NUM_CURVE_POINTS - 1`)
     store_packs<V>(prevp + 3 * PK, lvx); store_packs<V>(prevp + 4 * PK, lvy); store_packs<V>(prevp + 5 * PK, lvz);
     }   // step
+}
+
+// MULTI (grid off only): P.multi_steps steps in ONE launch.  Without the grid the strands never interact, so a thread simply
+// walks its strands again (its own stores of step k are its loads of step k+1; the state of a small scene sits in L1/L2);
+// the time-only wind scalars of every step come from the host-built P.wind_tab.  A 16K x 32 scene is launch- and
+// latency-bound (3.8 us of HBM time per step): this removes the launch, rvh_step_n uses it.
+template <int V, bool WIND, int NELL, int GATHER, bool MULTI = false>
+__global__ void __launch_bounds__(kBlock, (NELL <= -2 || GATHER == 2) ? RVH_K1X_MINBLOCKS : (GATHER ? RVH_K1G_MINBLOCKS : RVH_K1_MINBLOCKS))
+k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr,
+           const float4* __restrict__ fgrid, const __grid_constant__ CUtensorMap sdf_map, uint4* __restrict__ grid_clear, unsigned grid_clear_n) {
+    constexpr bool TMA = NELL == -3;
+    static_assert(!MULTI || (GATHER == 0 && !TMA), "several steps per launch need independent strands: no grid, no staged tiles");
+    // The step's grid clear (Renderer.cpp:2063) rides here when the launch is wide enough: this kernel never touches the
+    // int64 accumulators (it reads the float grid), the splat that fills them comes after it in the stream, and whoever
+    // read them last (finalize / exchange / a download) came before it.  Saves the memset launch.
+    if (grid_clear)
+        for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < grid_clear_n; k += gridDim.x * blockDim.x) grid_clear[k] = make_uint4(0u, 0u, 0u, 0u);
+    __shared__ __align__(128) unsigned char sdf_raw[TMA ? sizeof(SdfStageSmem) : 16];
+    SdfStageSmem& sm = *reinterpret_cast<SdfStageSmem*>(sdf_raw);
+    ftl_walk<V, WIND, NELL, GATHER, MULTI, MULTI>(P, planes, corr, fgrid, &sdf_map, sm, blockIdx.x, MULTI ? P.multi_steps : 1, 0);
 }
 
 // ---- K_splat: corrected velocities -> voxel grid (compute.comp:231-252) ----------------------------
@@ -879,23 +926,24 @@ __device__ __forceinline__ void splat_pack_ints(float2 sc2, float2 wx, float2 wy
 #ifndef RVH_SPLAT_MINBLOCKS
 #define RVH_SPLAT_MINBLOCKS 8
 #endif
-template <bool MAGIC>
-__global__ void __launch_bounds__(kSplatThreads, RVH_SPLAT_MINBLOCKS)
-k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid, int rows_per_chunk) {
+// The rows [1 + by * rows_per_chunk, ...) of the 128 strands of block bx.  COH: coherent loads of the planes (k_scene_step: the
+// same launch wrote them).
+template <bool MAGIC, bool COH>
+__device__ __forceinline__ void splat_rows(const StepParams& P, const float* __restrict__ planes, unsigned long long* __restrict__ grid, int rows_per_chunk,
+                                           int bx, int by, SplatStage (&stage)[kSplatThreads / 32][2]) {
     constexpr unsigned kFull = 0xffffffffu;
-    __shared__ SplatStage stage[kSplatThreads / 32][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s = P.strand0 + blockIdx.x * kSplatThreads + threadIdx.x;   // S_pad is a multiple of 128: always in bounds
+    const int s = P.strand0 + bx * kSplatThreads + threadIdx.x;   // S_pad is a multiple of 128: always in bounds
     const bool live = s < P.S;
     if (!__any_sync(kFull, live)) return;
-    const int r0 = 1 + blockIdx.y * rows_per_chunk, r1 = min(P.N, r0 + rows_per_chunk);
+    const int r0 = 1 + by * rows_per_chunk, r1 = min(P.N, r0 + rows_per_chunk);
     if (r0 >= r1) return;
     const int ca = lane & 1, cb = (lane >> 1) & 1, cc = (lane >> 2) & 1, slot = lane >> 3;
     const size_t RS = (size_t)P.S_pad * 6;
     const float* nextp = planes + tiled_index(6, P.S_pad, r0, 0, s);
     float nx[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
+    for (int k = 0; k < 6; ++k) nx[k] = ld_plane<COH>(nextp + k * kTileStrands);
     const float2 sc2 = make_float2(P.scale, P.scale);
     for (int r = r0; r < r1; ++r) {
         float c[6];
@@ -904,7 +952,7 @@ k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ pla
         nextp += RS;
         if (r + 1 < r1) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) nx[k] = __ldg(nextp + k * kTileStrands);
+            for (int k = 0; k < 6; ++k) nx[k] = ld_plane<COH>(nextp + k * kTileStrands);
         }
         // ---- phase A: lane = strand -------------------------------------------------------------------
         // t = RM(g + 1.5*2^23) = 1.5*2^23 + floor(g) for |g| < 2^22: fl = t - 1.5*2^23 is floor(g) as a float and
@@ -923,7 +971,16 @@ k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ pla
             w1[a] = __fadd_rn(__fsub_rn(g, __fadd_rn(fl, 1.0f)), 1.0f);
         }
         const float vinf = fmaxf(fabsf(c[3]), fmaxf(fabsf(c[4]), fabsf(c[5])));
-        const bool agg = touches && vinf <= P.splat_vagg;             // a NaN velocity fails the test
+        bool agg = touches && vinf <= P.splat_vagg;                   // a NaN velocity fails the test
+        if (P.splat_sparse) {
+            // Sparse hair (few strands per cell: the shipped 900-strand scene puts a row's 32 points into 20-30 cells): the aggregation
+            // below would take a pass per two cells (~170 instructions each, 6.4 us per row measured in k_scene_step); 32 atomics per
+            // point, all lanes at once, are ~200 instructions for the whole row.  Same integers (64-bit conversions of the same floats).
+            const int k0 = agg ? splat_key(f1[0], f1[1], f1[2]) : -1;
+            const unsigned same = __match_any_sync(kFull, k0);
+            const int distinct = __popc(__ballot_sync(kFull, agg && (__ffs(same) - 1 == lane)));
+            if (distinct >= P.splat_sparse) agg = false;               // warp-uniform
+        }
         const int key = agg ? splat_key(f1[0], f1[1], f1[2]) : -1;
         if (touches && !agg) {                                          // very fast (or NaN) point: 64-bit path, on its own
             const float wx[2] = { w0[0], w1[0] }, wy[2] = { w0[1], w1[1] }, wz[2] = { w0[2], w1[2] };
@@ -995,22 +1052,101 @@ k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ pla
     }
 }
 
+template <bool MAGIC>
+__global__ void __launch_bounds__(kSplatThreads, RVH_SPLAT_MINBLOCKS)
+k_grid_splat(const __grid_constant__ StepParams P, const float* __restrict__ planes, unsigned long long* __restrict__ grid, int rows_per_chunk) {
+    __shared__ SplatStage stage[kSplatThreads / 32][2];
+    splat_rows<MAGIC, false>(P, planes, grid, rows_per_chunk, blockIdx.x, blockIdx.y, stage);
+}
+
 // ---- grid finalize: int64 accumulators -> float cells for the gather ---------------------------
-// cell = (float(vel) * (1 / float(density))) per component, zero where density <= 0 (compute.comp:276-286).
 __global__ void __launch_bounds__(256)
 k_grid_finalize(const long long* __restrict__ grid, float4* __restrict__ fgrid, int cells, int int32_wrap) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cells) return;
     const longlong2* c = reinterpret_cast<const longlong2*>(grid + 4 * (size_t)k);
-    const longlong2 v01 = c[0], v2d = c[1];
-    long long dens = v2d.y, v0 = v01.x, v1 = v01.y, v2 = v2d.x;
-    if (int32_wrap) { dens = (int)dens; v0 = (int)v0; v1 = (int)v1; v2 = (int)v2; }   // the reference's int32 GridCell
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (dens > 0) {
-        const float rd = __frcp_rn(__ll2float_rn(dens));                 // 1.0 / float(density), compute.comp:283
-        o.x = __ll2float_rn(v0) * rd; o.y = __ll2float_rn(v1) * rd; o.z = __ll2float_rn(v2) * rd; o.w = __ll2float_rn(dens);
+    fgrid[k] = finalize_cell(c[0], c[1], int32_wrap);
+}
+
+// ---- small scenes: the WHOLE step -- several steps -- in one persistent cooperative launch ---------------------------------
+// The reference's shipped scene (900 strands x 10 points) and anything of that order is bound by launches and by dependent
+// latencies, not by bytes: replayed as a CUDA graph its 4 kernels take 28 us per step, 12 of them the FTL chain with the fused
+// gather (an L2 round trip and ~100 dependent instructions per row sit on the root->tip chain).  Here one co-resident grid of
+// CTAs walks the phases of a step with grid-wide barriers in between (scene_barrier), and the gather leaves the chain:
+//   1  CTAs [0, k1_ctas): integrate + collide + FTL WITHOUT gather (ftl_walk, as k_ftl_step<..., GATHER = 0>);
+//      all other CTAs meanwhile clear the int64 accumulators (Renderer.cpp:2063) -- the clear hides under the FTL chain;
+//   2  every CTA: splat (splat_rows over (strand block, row chunk) items, as k_grid_splat);
+//   3  every CTA: gather + friction, one thread per point, i.e. fully parallel, reading the int64
+//      accumulators directly (ld_cell<2> converts a cell as k_grid_finalize would: no finalize pass, no float grid).
+// Later phases read what earlier phases of the SAME launch wrote from other SMs (planes, grid): every such load is a coherent
+// ld.global (COH / SRC flavours above), never the read-only path; the grid barrier's fence orders them.  The time-only wind scalars
+// of each step come from P.wind_tab (host-evaluated, as MULTI).  Entry condition (host): no gather pending.  On exit the
+// accumulators hold the last step's grid (rvh_download_grid), the velocities are final (gather applied) and the float grid is stale.
+// Grid-wide barrier of a cooperative launch (all CTAs co-resident): one release-add per CTA on a monotonic counter, thread 0 spins
+// with acquire loads until the counter reaches this barrier's target.  The bar.sync on either side extends the release / acquire
+// to the CTA's other threads (cumulativity); the acquire invalidates the SM's L1, so the weak loads that follow see the other
+// CTAs' writes.  The host sizes the launch to the scene (tens of CTAs, not 148 x k): the barrier costs ~1 us there, where
+// cooperative_groups' grid.sync() over 296 CTAs was measured at ~6 us (profiles/r02 summary).
+__device__ __forceinline__ void scene_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - target) < 0);
     }
-    fgrid[k] = o;
+    __syncthreads();
+}
+
+template <int V, bool WIND, int NELL>
+__global__ void __launch_bounds__(kBlock, 2)
+k_scene_step(const __grid_constant__ StepParams P, float* planes, float* corr, unsigned long long* grid,
+             int nsteps, int k1_ctas, int splat_bx, int splat_items, int rows_per_chunk, unsigned* bar_counter, unsigned bar_base,
+             unsigned long long* timing) {                         // timing (RVH_SCENE_TIMING, tuning): CTA 0's %globaltimer at every phase boundary
+    static_assert(kSplatThreads == kBlock, "one block shape for all phases");
+    unsigned bar_target = bar_base;
+    int tick = 0;
+    auto stamp = [&]() {
+        if (timing && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); timing[tick++] = t; }
+    };
+    stamp();
+    __shared__ SplatStage stage[kSplatThreads / 32][2];
+    __shared__ __align__(128) unsigned char sdf_raw[16];
+    SdfStageSmem& sm = *reinterpret_cast<SdfStageSmem*>(sdf_raw);
+    const int cells = P.G * P.G * P.G;
+    constexpr int plane = kTileStrands;
+    const int points = (P.N - 1) * P.S_pad;
+    for (int step = 0; step < nsteps; ++step) {
+        if ((int)blockIdx.x < k1_ctas) {
+            ftl_walk<V, WIND, NELL, 0, true, true>(P, planes, corr, nullptr, nullptr, sm, blockIdx.x, 1, step);
+        } else {
+            uint4* gc = reinterpret_cast<uint4*>(grid);
+            const unsigned n = 2u * (unsigned)cells, stride = (gridDim.x - k1_ctas) * blockDim.x;
+            for (unsigned k = (blockIdx.x - k1_ctas) * blockDim.x + threadIdx.x; k < n; k += stride) gc[k] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        stamp();
+        scene_barrier(bar_counter, bar_target += gridDim.x);
+        stamp();
+        for (int item = blockIdx.x; item < splat_items; item += gridDim.x) {
+            splat_rows<true, true>(P, planes, grid, rows_per_chunk, item % splat_bx, item / splat_bx, stage);
+            __syncwarp();                                               // the next item reuses this warp's stage buffers
+        }
+        stamp();
+        scene_barrier(bar_counter, bar_target += gridDim.x);
+        stamp();
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < points; k += gridDim.x * blockDim.x) {
+            const int row = k / P.S_pad, s0 = k - row * P.S_pad;       // one thread per point: the phase is a latency chain, not bytes
+            if (s0 >= P.S) continue;
+            float* q = planes + tiled_index(6, P.S_pad, row + 1, 0, s0);     // skip the root row
+            float px = ld_plane<true>(q), py = ld_plane<true>(q + plane), pz = ld_plane<true>(q + 2 * plane);
+            float vx = ld_plane<true>(q + 3 * plane), vy = ld_plane<true>(q + 4 * plane), vz = ld_plane<true>(q + 5 * plane);
+            unsigned cand;
+            gather_pack<float, false, false, 2>(P, reinterpret_cast<const float4*>(grid), px, py, pz, vx, vy, vz, cand);
+            q[3 * plane] = vx; q[4 * plane] = vy; q[5 * plane] = vz;
+        }
+        stamp();
+        scene_barrier(bar_counter, bar_target += gridDim.x);
+        stamp();
+    }
 }
 
 // ---- multi-GPU: fused grid exchange over NVLink peer memory ---------------------------------------

@@ -147,6 +147,14 @@ def _fresh(S, N, L, flags, st, cols, spt=0):
     return sim
 
 
+def _plain(monkeypatch, S, N, L, flags, st, cols, spt=0):
+    """A context whose steps never take the persistent small-scene kernel (k_scene_step): the launch-per-kernel path."""
+    monkeypatch.setenv("RVH_SCENE_CTAS", "0")                   # read by rvh_create
+    sim = _fresh(S, N, L, flags, st, cols, spt)
+    monkeypatch.delenv("RVH_SCENE_CTAS")
+    return sim
+
+
 @pytest.mark.parametrize("S,N,flags,spt", [(16384, 32, rvh.WIND_B, 0), (16384, 32, rvh.WIND_B, 2), (3000, 16, rvh.WIND_A, 1), (900, 10, 0, 0)])
 def test_step_n_without_grid_runs_many_steps_per_launch_with_the_same_result(S, N, flags, spt):
     """Grid off: rvh_step_n puts up to 32 steps into ONE launch (k_ftl_step<..., MULTI>, per-step wind scalars from a host
@@ -170,11 +178,12 @@ def test_step_n_without_grid_runs_many_steps_per_launch_with_the_same_result(S, 
     assert np.array_equal(bits(fa), bits(fc)), "multi-step launch differs from single steps"
 
 
-def test_step_n_replays_a_cuda_graph_on_small_grid_scenes_with_the_same_result(golden_c1):
-    """Grid on, wind off, small scene (the shipped C1 scene): rvh_step_n captures one steady-state step as a CUDA graph and
-    replays it.  Same kernels, same order: bit-identical to calling rvh_step."""
+def test_step_n_replays_a_cuda_graph_on_small_grid_scenes_with_the_same_result(golden_c1, monkeypatch):
+    """Grid on, wind off, small scene (the shipped C1 scene) with the persistent kernel switched off: rvh_step_n captures one
+    steady-state step as a CUDA graph and replays it.  Same kernels, same order: bit-identical to calling rvh_step."""
     st, cols = golden_c1["state0"], golden_c1["colliders"]
     flags = rvh.GRID_ON | rvh.GRID_INT32_WRAP
+    monkeypatch.setenv("RVH_SCENE_CTAS", "0")
     a = rvh.HairSim(rvh.default_config(900, 10, flags=flags)); a.set_colliders(cols); a.upload(st)
     b = rvh.HairSim(rvh.default_config(900, 10, flags=flags)); b.set_colliders(cols); b.upload(st)
     a.step_n(25, DT, 0.0)
@@ -261,17 +270,20 @@ def test_resident_steps_after_a_pipelined_host_step_run_on_morton_order_again():
     a = rvh.HairSim(rvh.default_config(S, N, flags=flags)); a.set_colliders(cols)
     buf = st.copy()
     a.step_host(buf, DT, 0.1)
+    a.step(DT, 0.15)                                            # the first resident step re-sorts (not timed)
     ms_a = a.step_n(20, DT, 0.2) / 20
     fa = a.download()
     a.close()
     b = _fresh(S, N, L, flags, st, cols)
     b.step(DT, 0.1)
     b.upload(b.download())
+    b.step(DT, 0.15)
     ms_b = b.step_n(20, DT, 0.2) / 20
     fb = b.download()
     b.close()
     assert np.array_equal(bits(fa[:, 0:2]), bits(fb[:, 0:2]))
-    assert ms_a <= 1.5 * ms_b + 0.05, "resident steps after rvh_step_host are slow: %.3f ms vs %.3f ms" % (ms_a, ms_b)
+    # on unsorted strands the splat alone is ~10x slower: a factor of two separates the cases with room for timing noise
+    assert ms_a <= 2.0 * ms_b + 0.05, "resident steps after rvh_step_host are slow: %.3f ms vs %.3f ms" % (ms_a, ms_b)
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 33, 65])
@@ -294,10 +306,11 @@ def test_step_n_batch_edges_with_correction_vectors(n):
 
 
 @pytest.mark.parametrize("flags", [rvh.GRID_ON | rvh.REPULSION_ON, rvh.GRID_ON | rvh.KEEP_CORRECTION, rvh.GRID_ON | rvh.GRID_INT32_WRAP])
-def test_graph_replay_with_extension_and_layout_flags(flags):
+def test_graph_replay_with_extension_and_layout_flags(flags, monkeypatch):
     S, N = 6000, 16
     cols = rvh.scenes.bench_colliders()
     st = rvh.scenes.synthetic_head(S, N, 2.5, colliders=cols)
+    monkeypatch.setenv("RVH_SCENE_CTAS", "0")                   # the graph path (k_scene_step would take the last two flag sets)
     a, b = _fresh(S, N, 2.5, flags, st, cols), _fresh(S, N, 2.5, flags, st, cols)
     a.step_n(9, DT, 0.0)
     for k in range(9):
@@ -326,3 +339,63 @@ def test_pipelined_step_host_uneven_chunks_and_extensions(monkeypatch):
     sim.step_host(buf, DT, 0.2)
     sim.close()
     assert np.array_equal(bits(buf[:, 0:2]), bits(ref[:, 0:2]))
+
+
+# ---- small scenes: whole steps inside one persistent cooperative launch (k_scene_step) -------------------------------------
+
+@pytest.mark.parametrize("S,N,flags,spt", [(900, 10, rvh.GRID_ON | rvh.GRID_INT32_WRAP, 0), (3000, 16, rvh.GRID_ON | rvh.WIND_A, 1),
+                                           (6000, 16, rvh.GRID_ON | rvh.WIND_B | rvh.KEEP_CORRECTION, 2), (9000, 32, rvh.GRID_ON | rvh.WIND_B, 0),
+                                           (18000, 8, rvh.GRID_ON, 2)])
+def test_scene_step_kernel_equals_launch_per_kernel_steps(S, N, flags, spt, monkeypatch):
+    """rvh_step_n on a small grid scene: the steps run inside k_scene_step, up to 32 per launch -- FTL without gather | grid barrier |
+    splat | grid barrier | fully parallel gather straight from the int64 accumulators | grid barrier, the grid clear riding on the
+    CTAs the FTL phase leaves idle, per-step wind scalars from the host table.  40 steps == 40 launch-per-kernel steps (fused
+    gather through the finalized float grid), bit for bit, state and integer grid."""
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, 2.5, colliders=cols)
+    a = _fresh(S, N, 2.5, flags, st, cols, spt)
+    la = a.kernel_launches()
+    a.step_n(40, DT, 0.25)
+    used = a.kernel_launches() - la
+    fa, ga = a.download(), a.download_grid()
+    a.close()
+    b = _plain(monkeypatch, S, N, 2.5, flags, st, cols, spt)
+    t = np.float32(0.25)
+    lb = b.kernel_launches()
+    for k in range(40):
+        b.step(DT, float(t))
+        t = np.float32(t + np.float32(DT))
+    plain_used = b.kernel_launches() - lb
+    fb, gb = b.download(), b.download_grid()
+    b.close()
+    assert used == 2 and plain_used >= 3 * 40, (used, plain_used)    # 32 + 8 steps
+    assert np.array_equal(bits(fa), bits(fb)), "persistent small-scene kernel differs from launch-per-kernel steps"
+    assert np.array_equal(ga, gb)
+    assert np.abs(ga).max() > 0
+
+
+def test_rvh_step_takes_one_launch_per_step_on_a_small_scene(golden_c1, monkeypatch):
+    """The per-frame call itself (rvh_step, as Renderer::Frame would issue it) on the shipped C1 scene:
+    one k_scene_step launch per step, same state and grid as the launch-per-kernel path; colliders moving between steps
+    (Scene::translateSphere) and a read-back in the middle do not disturb it."""
+    st, cols = golden_c1["state0"], np.array(golden_c1["colliders"], copy=True)
+    flags = rvh.GRID_ON | rvh.GRID_INT32_WRAP
+    a = rvh.HairSim(rvh.default_config(900, 10, flags=flags)); a.set_colliders(cols); a.upload(st)
+    monkeypatch.setenv("RVH_SCENE_CTAS", "0")
+    b = rvh.HairSim(rvh.default_config(900, 10, flags=flags)); b.set_colliders(cols); b.upload(st)
+    monkeypatch.delenv("RVH_SCENE_CTAS")
+    a.step(DT, 0.0); b.step(DT, 0.0)
+    per_step = []
+    for k in range(1, 12):
+        if k == 4:
+            cols2 = cols.copy(); cols2[0, 12:15] += np.float32(0.05)     # the sphere's translation column (Scene.cpp:110-136)
+            a.set_colliders(cols2); b.set_colliders(cols2)
+        if k == 7:
+            assert np.array_equal(bits(a.download()), bits(b.download()))   # applies the pending gather on both sides
+        l0 = a.kernel_launches()
+        a.step(DT, k * float(DT)); b.step(DT, k * float(DT))
+        per_step.append(a.kernel_launches() - l0)
+    fa, fb, ga, gb = a.download(), b.download(), a.download_grid(), b.download_grid()
+    a.close(); b.close()
+    assert np.array_equal(bits(fa), bits(fb)) and np.array_equal(ga, gb)
+    assert per_step == [1] * 11, per_step
