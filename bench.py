@@ -515,7 +515,7 @@ def measure(R, rvh, args, workload, steps, warmup, scaling, full):
     if R.world == 1 and not (flags & rvh.SDF_ON):
         if not grid_on and S * N * 24 <= 126e6:
             fast = "up to 32 steps per launch (k_ftl_step MULTI)"
-        elif grid_on and not (flags & rvh.REPULSION_ON) and 2 * (-(-(S_pad // (args.spt if args.spt in (1, 2) else (2 if S >= 65536 else 1))) // 128)) <= \
+        elif grid_on and not (flags & rvh.REPULSION_ON) and 2 * (-(-(S_pad // (args.spt if args.spt in (1, 2) else (2 if S >= 131072 else 1))) // 128)) <= \
                 torch.cuda.get_device_properties(R.local).multi_processor_count and os.environ.get("RVH_SCENE_CTAS", "2") != "0":
             fast = "up to 32 whole steps per persistent cooperative launch (k_scene_step: FTL + gather | splat | finalize with grid barriers)"
         elif grid_on and "wind" not in flags_s and S_pad * N <= (1 << 23):

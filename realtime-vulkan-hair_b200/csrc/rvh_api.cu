@@ -491,6 +491,8 @@ int do_step(rvh_ctx* ctx, float dt, float total_time, int phases, bool lazy) {
     }
     if ((phases & 2) && grid) {
         { int r = finalize_grid(ctx); if (r) return r; }
+        // (Late round 2: running the stand-alone gather right away on latency-bound mid-size scenes, so that k_ftl_step's chain loses
+        // the gather, was measured on C3 100K x 64: k_ftl_step 0.133 -> 0.084 ms, but k_grid_gather costs 0.059 ms: no gain.)
         if (!lazy || ctx->interop_aos) { int r = launch_gather(ctx); if (r) return r; }
     }
     if (ctx->interop_indirect) {                                        // compute.comp:126-130,302: the draw's vertexCount = strands
@@ -598,7 +600,10 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     if (const char* e = std::getenv("RVH_SPLAT_WARPS")) c->splat_target_warps = std::max(1, std::atoi(e));
     int V = cfg->strands_per_thread;
     if (V == 4) V = 2;                                             // round 1 shipped a 4-strand kernel: it spilled (79-106 local ops) and never won; the value is still accepted
-    if (V != 1 && V != 2) V = c->S >= 65536 ? 2 : 1;               // measured on B200: 2 strands per thread is fastest at scale
+    // measured on B200 (scripts/probes/spt_sweep.py, grid + wind, ms per step 1 vs 2 strands per thread): 100K x 64 0.235 / 0.258,
+    // 150K x 32 0.181 / 0.177, 250K x 32 0.259 / 0.254, 600K x 32 0.528 / 0.493, 1M x 32: 2 by 10 %.  Packs halve the issue slots, which
+    // pays once the launch is throughput-bound; a single wave of CTAs is a latency chain and wants twice the warps instead.
+    if (V != 1 && V != 2) V = c->S >= 131072 ? 2 : 1;
     c->V = V;
     std::memset(&c->sdf_map, 0, sizeof c->sdf_map);
     ctx = c;
@@ -651,9 +656,10 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
         P.splat_vagg = v;
     }
     P.keep_corr = c->corr ? 1 : 0;
-    // sparse hair: below ~64K strands a warp's 32 Morton neighbours stop sharing cells (RVH_SPLAT_SPARSE: the distinct-cell count
-    // from which a row is splatted point by point; 0 = never)
-    P.splat_sparse = c->S < 65536 ? 5 : 0;
+    // sparse hair: with a few thousand strands a warp's 32 Morton neighbours stop sharing cells (RVH_SPLAT_SPARSE: the distinct-cell
+    // count from which a row is splatted point by point; 0 = never).  Not for dense scenes: forced on at C3 (100K x 64) the 32 atomics
+    // per point take the splat from 0.136 to 0.305 ms.
+    P.splat_sparse = c->S < 16384 ? 5 : 0;
     if (const char* e = std::getenv("RVH_SPLAT_SPARSE")) P.splat_sparse = std::max(0, std::atoi(e));
 
     if (nranks > 1) {

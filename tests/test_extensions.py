@@ -201,7 +201,7 @@ def test_gpu_mesh_bake_matches_oracle():
 @pytest.mark.parametrize("S,N,L,extra,spt", [
     (6000, 32, 2.5, 0, 0),
     (6000, 32, 2.5, rvh.WIND_B | rvh.GRID_ON, 2),
-    (70000, 16, 2.5, rvh.GRID_ON, 0),        # S >= 65536: two strands per thread by default
+    (70000, 16, 2.5, rvh.GRID_ON, 2),        # two strands per thread (the default from 128K strands on)
     (3001, 24, 2.5, 0, 1),
     (900, 10, 2.5, rvh.GRID_ON, 0),
 ])
