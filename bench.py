@@ -514,7 +514,7 @@ def measure(R, rvh, args, workload, steps, warmup, scaling, full):
     fast = None
     if R.world == 1 and not (flags & rvh.SDF_ON):
         if not grid_on and S * N * 24 <= 126e6:
-            fast = "up to 32 steps per launch (k_ftl_step MULTI)"
+            fast = "up to 32 steps per launch (k_ftl_wave: wavefront over the steps on small scenes; k_ftl_step MULTI otherwise)"
         elif grid_on and not (flags & rvh.REPULSION_ON) and 2 * (-(-(S_pad // (args.spt if args.spt in (1, 2) else (2 if S >= 131072 else 1))) // 128)) <= \
                 torch.cuda.get_device_properties(R.local).multi_processor_count and os.environ.get("RVH_SCENE_CTAS", "2") != "0":
             fast = "up to 32 whole steps per persistent cooperative launch (k_scene_step: FTL + gather | splat | finalize with grid barriers)"

@@ -196,7 +196,7 @@ int rvh_step(rvh_ctx* ctx, float dt, float total_time);
 /* n back-to-back steps, total_time advancing by dt (float additions, exactly as n calls would); if ms_out != NULL the whole
  * batch is timed with CUDA events on the context's stream and the call synchronises.  Same results as n calls of rvh_step,
  * bit for bit; small scenes take a faster route to them: without the grid up to 32 steps ride in ONE kernel launch (the strands
- * never interact); with the grid, scenes of up to ~9.5K strands run whole steps (up to 32) inside ONE persistent cooperative launch
+ * never interact; small ones as a wavefront over the steps, k_ftl_wave: several lanes per strand, each a step ahead of the next); with the grid, scenes of up to ~9.5K strands run whole steps (up to 32) inside ONE persistent cooperative launch
  * (k_scene_step: FTL | splat | gather between grid-wide barriers; rvh_step takes the same kernel, one launch per step); larger
  * ones without wind capture the step once as a CUDA graph and replay it (nothing in its kernel parameters depends on time).
  * Per-kernel profiling (rvh_profile_enable) and RVH_NO_FAST_STEP_N=1 select plain stepping (RVH_SCENE_CTAS=0: no k_scene_step). */

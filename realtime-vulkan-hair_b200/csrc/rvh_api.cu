@@ -80,6 +80,7 @@ struct rvh_ctx {
     bool uploaded = false, colliders_set = false;
     unsigned long long* scene_timing = nullptr;                        // RVH_SCENE_TIMING=1: phase time stamps of CTA 0, printed after every launch (tuning)
     unsigned* scene_bar = nullptr; unsigned scene_bar_base = 0u;       // k_scene_step's grid barrier: monotonic device counter, its value before the next launch
+    int wave_steps = 1;                   // RVH_WAVE_STEPS=0 (tuning / A-B): grid-less small scenes take k_ftl_step<MULTI> instead of the step wavefront k_ftl_wave
     int scene_ctas_per_sm = 2;            // RVH_SCENE_CTAS env (tuning; 0 = off): CTAs per SM of the persistent small-scene kernel k_scene_step
     int splat_target_warps = 32768;       // RVH_SPLAT_WARPS env (tuning): the splat splits rows over blockIdx.y until it has this many warps
     // rvh_step_n fast paths for small scenes: several steps per launch (grid off), CUDA-graph replay of the step (grid on, wind off)
@@ -310,8 +311,26 @@ int launch_multi_step(rvh_ctx* ctx, int n, float dt, float& t) {      // t advan
         P.wind_tab[3 * k] = amp * s2T; P.wind_tab[3 * k + 1] = T3; P.wind_tab[3 * k + 2] = amp;
     }
     P.cta0 = 0;
-#define RVH_MULTI(V_, W_, NE_) k_ftl_step<V_, W_, NE_, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u)
     const bool five = P.n_ell == 5;       // the reference scene's collider count: unrolled tests (the kernel is latency-bound here: the unrolled tests overlap)
+    // Small scene (its k_ftl_step CTAs would leave the schedulers nearly empty): wavefront over the steps, W lanes per strand (k_ftl_wave)
+    const int wave_w = (ctx->V != 1 || n < 2 || ctx->N < 3 || !ctx->wave_steps) ? 0 : (ctx->k1_blocks * 8 <= 6 * ctx->num_sms ? 8 : (ctx->k1_blocks * 4 <= 6 * ctx->num_sms ? 4 : 0));
+    if (wave_w) {
+        const int blocks = ctx->S_pad * wave_w / kBlock;
+#define RVH_WAVE(W_, NE_, L_) k_ftl_wave<W_, NE_, L_><<<blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr)
+        if (wave_w == 8) {
+            if (five) { if (wind) RVH_WAVE(true, 5, 8); else RVH_WAVE(false, 5, 8); }
+            else      { if (wind) RVH_WAVE(true, -1, 8); else RVH_WAVE(false, -1, 8); }
+        } else {
+            if (five) { if (wind) RVH_WAVE(true, 5, 4); else RVH_WAVE(false, 5, 4); }
+            else      { if (wind) RVH_WAVE(true, -1, 4); else RVH_WAVE(false, -1, 4); }
+        }
+#undef RVH_WAVE
+        P.multi_steps = 1;
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+        return RVH_OK;
+    }
+#define RVH_MULTI(V_, W_, NE_) k_ftl_step<V_, W_, NE_, 0, true><<<ctx->k1_blocks, kBlock, 0, ctx->stream>>>(P, ctx->planes, ctx->corr, ctx->fgrid, ctx->sdf_map, nullptr, 0u)
     if (ctx->V == 2) {
         if (five) { if (wind) RVH_MULTI(2, true, 5); else RVH_MULTI(2, false, 5); }
         else      { if (wind) RVH_MULTI(2, true, -1); else RVH_MULTI(2, false, -1); }
@@ -596,6 +615,7 @@ int create_impl(rvh_ctx** out, const rvh_config* cfg, int rank, int nranks, cons
     c->S = cfg->num_strands; c->N = cfg->num_points;
     c->S_pad = ((c->S + kTileStrands - 1) / kTileStrands) * kTileStrands;
     c->rank = rank; c->nranks = nranks;
+    if (const char* e = std::getenv("RVH_WAVE_STEPS")) c->wave_steps = std::atoi(e) != 0;
     if (const char* e = std::getenv("RVH_SCENE_CTAS")) c->scene_ctas_per_sm = std::max(0, std::min(4, std::atoi(e)));
     if (const char* e = std::getenv("RVH_SPLAT_WARPS")) c->splat_target_warps = std::max(1, std::atoi(e));
     int V = cfg->strands_per_thread;

@@ -17,6 +17,7 @@
 //                                   behind the collider candidate mask, or the head SDF by plain loads / TMA-staged tiles),
 //                                   then integrate + FTL + corrected velocity.  MULTI (grid off): up to 32 whole steps per launch
 //   k_grid_splat<MAGIC>             two-phase register-accumulating integer splat, one RED.64 per lane and cell (sparse rows: point by point)
+//   k_ftl_wave<WIND,NELL,W>         grid off, small scene: wavefront over the steps (W lanes per strand, lane j = step s0+j, rows handed down by shuffles)
 //   k_scene_step<V,WIND,NELL>       small scenes: whole steps in ONE persistent cooperative launch (FTL || clear | splat | per-point gather
 //                                   from the raw accumulators, grid-wide barriers in between); rvh_step / rvh_step_n use it
 //   k_grid_exchange                 sharded runs: pull-reduce + finalize + push over NVLink peer memory (or ncclAllReduce); bounded waits
@@ -849,6 +850,78 @@ k_ftl_step(const __grid_constant__ StepParams P, float* __restrict__ planes, flo
     __shared__ __align__(128) unsigned char sdf_raw[TMA ? sizeof(SdfStageSmem) : 16];
     SdfStageSmem& sm = *reinterpret_cast<SdfStageSmem*>(sdf_raw);
     ftl_walk<V, WIND, NELL, GATHER, MULTI, MULTI>(P, planes, corr, fgrid, &sdf_map, sm, blockIdx.x, MULTI ? P.multi_steps : 1, 0);
+}
+
+// ---- grid off, small scene: a WAVEFRONT over the steps -------------------------------------------------------------------
+// k_ftl_step<..., MULTI> removes the launches of a small grid-less scene (C2: 16K x 32), but each of its threads still walks 31
+// dependent rows per step, and 128 CTAs put one warp on a scheduler: ~0.5 us per row of pure dependent-issue latency, 16 us per step
+// on an idle machine.  The root->tip chain cannot be split -- but consecutive STEPS can overlap: row i of step s+1 needs nothing but
+// row i of step s (its final velocity, i.e. once step s has passed row i+1: compute.comp:213-215) and its own row i-1.  So W lanes
+// share a strand, lane j runs step s0+j, two rows behind lane j-1:
+//     tick k:  lane j updates row i = k - 2j (if 1 <= i <= N-1) and finalises the velocity of row i-1 (row N: just publishes the last one)
+//     end of tick:  __shfl_up hands (new position of row i, final velocity of row i-1) to lane j+1, which uses the position two ticks
+//                   and the velocity one tick later; lane 0 reads the rows from memory (one row prefetched), the last active lane writes them.
+// W steps take (N-1) + 2(W-1) + 1 ticks instead of W(N-1), and the launch has W times the warps: the ticks of 3-4 warps per scheduler
+// overlap.  Same device function per point (point_update<float, ...>) and the same operations as single steps: bit-identical.
+// A warp = 32/W strands x W lanes; between batches of W steps the warp re-reads its own stores (coherent loads after __syncwarp).
+template <bool WIND, int NELL, int W>
+__global__ void __launch_bounds__(kBlock, 4)
+k_ftl_wave(const __grid_constant__ StepParams P, float* __restrict__ planes, float* __restrict__ corr) {
+    static_assert(W == 4 || W == 8, "lanes per strand");
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr int PK = kTileStrands;
+    const int lane = threadIdx.x & 31, j = lane % W;
+    const int s = (blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * (32 / W) + lane / W;   // strand of this lane group
+    const bool live = s < P.S_pad;                               // whole groups are live or not; dead groups still take part in the shuffles
+    const int sc = live ? s : 0;
+    const size_t RS = (size_t)P.S_pad * 6;
+    float* const base = planes + tiled_index(6, P.S_pad, 0, 0, sc);
+    const float rx = base[0], ry = base[PK], rz = base[2 * PK];  // the root never moves
+    const float minus_inv_dt = -P.inv_dt;
+    const SdfTile no_tile = { nullptr, 0, 0, 0 };
+    const int ticks = (P.N - 1) + 2 * (W - 1) + 1;
+    for (int s0 = 0; s0 < P.multi_steps; s0 += W) {
+        const int nb = min(W, P.multi_steps - s0);               // steps of this batch: lanes j >= nb idle
+        const bool mine = live && j < nb, first = j == 0, last = j == nb - 1;
+        const int step = min(s0 + j, P.multi_steps - 1);
+        const WindNow Wn = { P.wind_tab[3 * step], P.wind_tab[3 * step + 1], P.wind_tab[3 * step + 2] };
+        float parx = rx, pary = ry, parz = rz;                    // this step's position of row i-1
+        float lvx = 0.f, lvy = 0.f, lvz = 0.f;                    // its clamped velocity, correction pending
+        float hx = 0.f, hy = 0.f, hz = 0.f, nx_ = 0.f, ny_ = 0.f, nz_ = 0.f;   // positions handed down by lane j-1: row of the next tick / the one after
+        float ivx = 0.f, ivy = 0.f, ivz = 0.f;                    // final velocity handed down for the row of the next tick
+        float mx = 0.f, my = 0.f, mz = 0.f, mvx = 0.f, mvy = 0.f, mvz = 0.f;   // lane 0: row prefetched from memory
+        const float* rd = base + RS;
+        if (first && mine) { mx = rd[0]; my = rd[PK]; mz = rd[2 * PK]; mvx = rd[3 * PK]; mvy = rd[4 * PK]; mvz = rd[5 * PK]; }
+        for (int k = 1; k <= ticks; ++k) {
+            const int i = k - 2 * j;
+            float cx, cy, cz, vx, vy, vz;
+            if (first) {
+                cx = mx; cy = my; cz = mz; vx = mvx; vy = mvy; vz = mvz;
+                rd += RS;
+                if (mine && i + 1 < P.N) { mx = rd[0]; my = rd[PK]; mz = rd[2 * PK]; mvx = rd[3 * PK]; mvy = rd[4 * PK]; mvz = rd[5 * PK]; }
+            } else { cx = hx; cy = hy; cz = hz; vx = ivx; vy = ivy; vz = ivz; }
+            float opx = 0.f, opy = 0.f, opz = 0.f, ofx = lvx, ofy = lvy, ofz = lvz;   // row N: the last velocity has no correction (compute.comp:213)
+            if (mine && i >= 1 && i < P.N) {
+                const PointOut<float> o = point_update<float, WIND, NELL, 0>(P, Wn, no_tile, nullptr, cx, cy, cz, vx, vy, vz, parx, pary, parz);
+                parx = o.px; pary = o.py; parz = o.pz;
+                opx = o.px; opy = o.py; opz = o.pz;
+                ofx = fmaf(o.dx, minus_inv_dt, lvx); ofy = fmaf(o.dy, minus_inv_dt, lvy); ofz = fmaf(o.dz, minus_inv_dt, lvz);   // v_{i-1} -= d_i / dt
+                lvx = o.vx; lvy = o.vy; lvz = o.vz;
+                if (last) {
+                    float* w = base + (size_t)i * RS;
+                    w[0] = o.px; w[PK] = o.py; w[2 * PK] = o.pz;
+                    if (P.keep_corr) { float* c0 = corr + tiled_index(3, P.S_pad, i, 0, sc); c0[0] = o.dx; c0[PK] = o.dy; c0[2 * PK] = o.dz; }
+                }
+            }
+            if (mine && last && i >= 2 && i <= P.N) { float* w = base + (size_t)(i - 1) * RS; w[3 * PK] = ofx; w[4 * PK] = ofy; w[5 * PK] = ofz; }
+            // hand (position of row i, final velocity of row i-1) to lane j+1
+            const float tpx = __shfl_up_sync(kFull, opx, 1, W), tpy = __shfl_up_sync(kFull, opy, 1, W), tpz = __shfl_up_sync(kFull, opz, 1, W);
+            ivx = __shfl_up_sync(kFull, ofx, 1, W); ivy = __shfl_up_sync(kFull, ofy, 1, W); ivz = __shfl_up_sync(kFull, ofz, 1, W);
+            hx = nx_; hy = ny_; hz = nz_;
+            nx_ = tpx; ny_ = tpy; nz_ = tpz;
+        }
+        __syncwarp();                                             // the next batch's lane 0 reads what this batch's last lane wrote
+    }
 }
 
 // ---- K_splat: corrected velocities -> voxel grid (compute.comp:231-252) ----------------------------

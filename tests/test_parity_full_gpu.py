@@ -399,3 +399,34 @@ def test_rvh_step_takes_one_launch_per_step_on_a_small_scene(golden_c1, monkeypa
     a.close(); b.close()
     assert np.array_equal(bits(fa), bits(fb)) and np.array_equal(ga, gb)
     assert per_step == [1] * 11, per_step
+
+
+# ---- grid off, small scenes: the wavefront over the steps (k_ftl_wave) ------------------------------------------------------
+
+@pytest.mark.parametrize("S,N,n,flags", [(16384, 5, 7, rvh.WIND_B), (16384, 8, 6, rvh.WIND_A | rvh.KEEP_CORRECTION), (16000, 32, 5, 0),
+                                         (1000, 3, 9, rvh.WIND_B), (1000, 4, 17, rvh.WIND_B | rvh.KEEP_CORRECTION), (27000, 16, 40, rvh.WIND_B),
+                                         (300, 2, 5, rvh.WIND_B)])
+def test_step_wavefront_partial_batches_short_strands_same_bits(S, N, n, flags, monkeypatch):
+    """k_ftl_wave: W = 4 or 8 lanes share a strand, lane j runs step s0 + j two rows behind lane j - 1.  Partial batches (n not a
+    multiple of W), the shortest strands (N = 3: one interior row; N = 2 falls back to the many-steps kernel), both lane counts
+    (16K strands -> 4 lanes, 1K -> 8): bit-identical to single steps AND to the many-steps kernel k_ftl_step<MULTI>."""
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, 2.5, colliders=cols)
+    a = _fresh(S, N, 2.5, flags, st, cols)
+    la = a.kernel_launches()
+    a.step_n(n, DT, 0.5)
+    assert a.kernel_launches() - la == (n + 31) // 32
+    fa = a.download(); a.close()
+    monkeypatch.setenv("RVH_WAVE_STEPS", "0")
+    m = _fresh(S, N, 2.5, flags, st, cols)
+    monkeypatch.delenv("RVH_WAVE_STEPS")
+    m.step_n(n, DT, 0.5)
+    fm = m.download(); m.close()
+    b = _fresh(S, N, 2.5, flags, st, cols)
+    t = np.float32(0.5)
+    for k in range(n):
+        b.step(DT, float(t))
+        t = np.float32(t + np.float32(DT))
+    fb = b.download(); b.close()
+    assert np.array_equal(bits(fa), bits(fb)), "step wavefront differs from single steps"
+    assert np.array_equal(bits(fm), bits(fb)), "many-steps kernel differs from single steps"
