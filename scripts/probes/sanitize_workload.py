@@ -67,3 +67,22 @@ sim.step(DT, 0.0); sim.step(DT, 0.1); sim.sync()
 assert ind.cpu().tolist() == [S, 1, 0, 0]
 sim.close()
 print("ok interop hook", flush=True)
+
+# ---- late round 2: persistent small-scene kernel (k_scene_step), sparse-row splat, step wavefront (k_ftl_wave), graph replay kept reachable
+for S, N, flags, spt, env in ((900, 10, rvh.GRID_ON | rvh.GRID_INT32_WRAP, 0, {}), (3000, 12, rvh.GRID_ON | rvh.WIND_B | rvh.KEEP_CORRECTION, 2, {}),
+                              (900, 10, rvh.GRID_ON, 0, {"RVH_SCENE_CTAS": "0"}), (16384, 6, rvh.WIND_B, 1, {}), (1000, 3, rvh.WIND_A | rvh.KEEP_CORRECTION, 0, {})):
+    os.environ.update(env)
+    sim = rvh.HairSim(rvh.default_config(S, N, flags=flags, strands_per_thread=spt))
+    for k in env:
+        del os.environ[k]
+    sim.set_colliders(cols)
+    sim.upload(rvh.scenes.synthetic_head(S, N, 2.5))
+    sim.step(DT, 0.0)
+    sim.step_n(35, DT, 0.1)
+    sim.step_n(3, DT, 1.0)
+    sim.step(DT, 1.2)
+    assert np.isfinite(sim.download()).all()
+    if flags & rvh.GRID_ON:
+        assert np.abs(sim.download_grid()).max() > 0
+    sim.close()
+    print("ok late paths", S, N, flags, spt, env, flush=True)
