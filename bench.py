@@ -517,7 +517,7 @@ def measure(R, rvh, args, workload, steps, warmup, scaling, full):
             fast = "up to 32 steps per launch (k_ftl_wave: wavefront over the steps on small scenes; k_ftl_step MULTI otherwise)"
         elif grid_on and not (flags & rvh.REPULSION_ON) and 2 * (-(-(S_pad // (args.spt if args.spt in (1, 2) else (2 if S >= 131072 else 1))) // 128)) <= \
                 torch.cuda.get_device_properties(R.local).multi_processor_count and os.environ.get("RVH_SCENE_CTAS", "2") != "0":
-            fast = "up to 32 whole steps per persistent cooperative launch (k_scene_step: FTL + gather | splat | finalize with grid barriers)"
+            fast = "up to 32 whole steps per persistent cooperative launch (k_scene_step: FTL without gather || clear | splat | per-point gather from the int64 accumulators, grid barriers in between)"
         elif grid_on and "wind" not in flags_s and S_pad * N <= (1 << 23):
             fast = "CUDA-graph replay of the step"
     small = fast is not None
@@ -562,11 +562,15 @@ def measure(R, rvh, args, workload, steps, warmup, scaling, full):
     dominant = max(per_kernel, key=lambda k: per_kernel[k])
     # graph replay: the kernel is the same as in the per-kernel pass, its duration comes from there; many-steps-per-launch: the
     # launch IS the steps, so the step time of the timed region is the per-step duration of the kernel
-    k1_ms = per_kernel["ftl_step"] if (kernel_events or (small and grid_on and per_kernel["ftl_step"])) else ms / steps
+    scene = bool(fast) and fast.startswith("up to 32 whole steps")          # k_scene_step: the launch IS the steps, all phases inside
+    k1_ms = per_kernel["ftl_step"] if (kernel_events or (small and grid_on and not scene and per_kernel["ftl_step"])) else ms / steps
     # every kernel of the step with its ALGORITHMIC bytes per launch (fp32 xyz only) and CUDA-event duration
     kernels = {"k_ftl_step": {"what": "integrate + collide + FTL + corrected velocity%s" % (" + fused gather of the previous grid" if grid_on else ""),
                               "algorithmic_bytes_per_launch": S * b1, "avg_launch_ms": k1_ms, "bound": "hbm"}}
-    if grid_on and per_kernel.get("grid_splat"):
+    if scene:
+        kernels = {"k_scene_step": {"what": "the whole step in one persistent launch: integrate + collide + FTL || grid clear | splat | gather from the int64 accumulators",
+                                    "algorithmic_bytes_per_launch": S * (b1 + b2), "avg_launch_ms": k1_ms, "bound": "hbm (scored against it; the launch is latency-bound: three grid barriers and a 9-row dependent chain)"}}
+    elif grid_on and per_kernel.get("grid_splat"):
         # reads p, v of every moving point once; its time is integer work (32 float->int truncations + adds per point), not bytes
         kernels["k_grid_splat"] = {"what": "corrected velocities -> int64 voxel grid (compute.comp:231-252)", "algorithmic_bytes_per_launch": S * (N - 1) * 24,
                                    "avg_launch_ms": per_kernel["grid_splat"], "bound": "issue (scored against hbm: the roofline the contract allows)"}
@@ -578,10 +582,10 @@ def measure(R, rvh, args, workload, steps, warmup, scaling, full):
     roofline = {"bound": "hbm", "kernel": "%s (%s)" % (dom, D["what"]),
                 "achieved": D["achieved"], "peak": peak, "unit": "GB/s", "frac": D["frac"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": D["algorithmic_bytes_per_launch"], "avg_launch_ms": D["avg_launch_ms"],
-                "kernels": kernels, "north_star_kernel": "k_ftl_step", "north_star_frac": kernels["k_ftl_step"]["frac"],
+                "kernels": kernels, "north_star_kernel": "k_scene_step" if scene else "k_ftl_step", "north_star_frac": kernels["k_scene_step" if scene else "k_ftl_step"]["frac"],
                 "per_kernel_ms": per_kernel,
                 "per_kernel_ms_source": ("ftl_step: CUDA events inside the timed region; " if kernel_events else
-                                         "small scene: rvh_step_n replays the step as a CUDA graph (avg_launch_ms: k_ftl_step in the per-kernel pass) or runs many steps per launch (avg_launch_ms: step time of the timed region); ") +
+                                         "small scene: rvh_step_n replays the step as a CUDA graph (avg_launch_ms: k_ftl_step in the per-kernel pass) or runs many steps per launch (k_ftl_wave / k_ftl_step MULTI / k_scene_step; avg_launch_ms: step time of the timed region; the per-kernel pass below then shows the launch-per-kernel path, not the timed one); ") +
                                         "per_kernel_ms: events around every kernel in a separate pass of %d single steps right after it" % n2,
                 "longest_kernel": dominant, "sampler_overhead_ms_per_step": max(0.0, ms / steps - ms_plain),
                 "step_bytes": S * (b1 + b2), "step_frac": (S * (b1 + b2) / (ms / steps * 1e-3) / 1e9) / peak,
