@@ -345,7 +345,8 @@ def test_pipelined_step_host_uneven_chunks_and_extensions(monkeypatch):
 
 @pytest.mark.parametrize("S,N,flags,spt", [(900, 10, rvh.GRID_ON | rvh.GRID_INT32_WRAP, 0), (3000, 16, rvh.GRID_ON | rvh.WIND_A, 1),
                                            (6000, 16, rvh.GRID_ON | rvh.WIND_B | rvh.KEEP_CORRECTION, 2), (9000, 32, rvh.GRID_ON | rvh.WIND_B, 0),
-                                           (18000, 8, rvh.GRID_ON, 2)])
+                                           (18000, 8, rvh.GRID_ON, 2), (130, 2, rvh.GRID_ON | rvh.WIND_B, 0), (1, 5, rvh.GRID_ON, 0),
+                                           (257, 3, rvh.GRID_ON | rvh.GRID_INT32_WRAP | rvh.WIND_A, 2)])
 def test_scene_step_kernel_equals_launch_per_kernel_steps(S, N, flags, spt, monkeypatch):
     """rvh_step_n on a small grid scene: the steps run inside k_scene_step, up to 32 per launch -- FTL without gather | grid barrier |
     splat | grid barrier | fully parallel gather straight from the int64 accumulators | grid barrier, the grid clear riding on the
