@@ -1164,8 +1164,11 @@ __device__ __forceinline__ void scene_barrier(unsigned* counter, unsigned target
     __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
-        unsigned v;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - target) < 0);
+        unsigned v, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (++spins > (1u << 25)) __trap();                         // ~20 s: the launch is broken (a co-resident CTA never arrives); a trap is better than a hung GPU
+        } while ((int)(v - target) < 0);
     }
     __syncthreads();
 }

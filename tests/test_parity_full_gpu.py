@@ -431,3 +431,25 @@ def test_step_wavefront_partial_batches_short_strands_same_bits(S, N, n, flags, 
     fb = b.download(); b.close()
     assert np.array_equal(bits(fa), bits(fb)), "step wavefront differs from single steps"
     assert np.array_equal(bits(fm), bits(fb)), "many-steps kernel differs from single steps"
+
+
+def test_step_wavefront_against_the_oracle():
+    """The kernel the C2 bench line times (k_ftl_wave, 4 lanes per strand at 16K x 32), compared with the oracle directly: one
+    launch = 4 steps in flight at once, against 4 free-running oracle steps (chaos bound of SURVEY.md section 7, as the ten-step test)."""
+    S, N, L = 16384, 32, 2.5
+    cols = rvh.scenes.bench_colliders()
+    st = rvh.scenes.synthetic_head(S, N, L, colliders=cols)
+    sim = _fresh(S, N, L, rvh.WIND_B, st, cols)
+    l0 = sim.kernel_launches()
+    sim.step_n(4, DT, 0.5)
+    assert sim.kernel_launches() - l0 == 1
+    got = sim.download(); sim.close()
+    p = orc.default_params(S, N, orc.WIND_B, rest_length=np.float32(L) / np.float32(N - 1))
+    ref, t = st.copy(), np.float32(0.5)
+    for k in range(4):
+        ref, _ = orc.step(p, cols, DT, t, ref)
+        t = np.float32(t + np.float32(DT))
+    err = float(np.abs(got[:, 0, :, :3] - ref[:, 0, :, :3]).max()) / L
+    print("wavefront, 4 steps, max |dp| / L = %.2e" % err)
+    assert err <= 2e-5
+    assert np.array_equal(bits(got[:, 0, 0]), bits(ref[:, 0, 0]))
