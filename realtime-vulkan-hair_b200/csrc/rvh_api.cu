@@ -345,7 +345,7 @@ int launch_multi_step(rvh_ctx* ctx, int n, float dt, float& t) {      // t advan
     return RVH_OK;
 }
 
-// Small scene, grid on, gather pending: `n` steps (<= 32) in ONE cooperative launch of k_scene_step (see the kernel).
+// Small scene, grid on: `n` steps (<= 32) in ONE cooperative launch of k_scene_step (see the kernel).
 bool scene_step_eligible(const rvh_ctx* ctx) {
     const int flags = ctx->cfg.flags;
     return ctx->scene_ctas_per_sm > 0 && (flags & RVH_GRID_ON) && !(flags & (RVH_SDF_ON | RVH_REPULSION_ON)) && ctx->nranks == 1 &&
@@ -397,7 +397,7 @@ int launch_scene_steps(rvh_ctx* ctx, int n, float dt, float& t) {      // t adva
     if (per_sm < 1) return fail(ctx, RVH_ERR_CUDA, "k_scene_step does not fit on an SM");
     const int max_blocks = per_sm * ctx->num_sms;
     // The launch is sized to the scene, not to the machine: every barrier costs one atomic per CTA.  Enough CTAs for the FTL chains plus
-    // a clearing crew beside them, for one splat item (128 strands x a chunk of rows) per CTA, and for one gather pack per thread.
+    // a clearing crew beside them, for one splat item (128 strands x a chunk of rows) per CTA, and for one gather point per thread.
     const int splat_bx = ctx->S_pad / kSplatThreads, rows = ctx->N - 1;
     const int points = rows * ctx->S_pad;
     int blocks = std::max(ctx->k1_blocks + std::max(16, ctx->k1_blocks), (points + kBlock - 1) / kBlock);
