@@ -81,6 +81,7 @@ struct rvh_ctx {
     unsigned long long* scene_timing = nullptr;                        // RVH_SCENE_TIMING=1: phase time stamps of CTA 0, printed after every launch (tuning)
     unsigned* scene_bar = nullptr; unsigned scene_bar_base = 0u;       // k_scene_step's grid barrier: monotonic device counter, its value before the next launch
     int wave_steps = 1;                   // RVH_WAVE_STEPS=0 (tuning / A-B): grid-less small scenes take k_ftl_step<MULTI> instead of the step wavefront k_ftl_wave
+    int scene_occupancy[2][2] = { { 0, 0 }, { 0, 0 } };
     int scene_ctas_per_sm = 2;            // RVH_SCENE_CTAS env (tuning; 0 = off): CTAs per SM of the persistent small-scene kernel k_scene_step
     int splat_target_warps = 32768;       // RVH_SPLAT_WARPS env (tuning): the splat splits rows over blockIdx.y until it has this many warps
     // rvh_step_n fast paths for small scenes: several steps per launch (grid off), CUDA-graph replay of the step (grid on, wind off)
@@ -393,7 +394,9 @@ int launch_scene_steps(rvh_ctx* ctx, int n, float dt, float& t) {      // t adva
         P.wind_tab[3 * k] = amp * s2T; P.wind_tab[3 * k + 1] = T3; P.wind_tab[3 * k + 2] = amp;
     }
     P.cta0 = 0; P.strand0 = 0;
-    const int per_sm = std::min(ctx->scene_ctas_per_sm, scene_kernel_dispatch(ctx, wind, n, 0, 0, 0, 0));
+    int& occ = ctx->scene_occupancy[wind ? 1 : 0][P.n_ell == 5 ? 1 : 0];  // co-resident CTAs per SM of this kernel variant: asked once (the per-frame call counts its host microseconds)
+    if (occ == 0) occ = scene_kernel_dispatch(ctx, wind, n, 0, 0, 0, 0);
+    const int per_sm = std::min(ctx->scene_ctas_per_sm, occ);
     if (per_sm < 1) return fail(ctx, RVH_ERR_CUDA, "k_scene_step does not fit on an SM");
     const int max_blocks = per_sm * ctx->num_sms;
     // The launch is sized to the scene, not to the machine: every barrier costs one atomic per CTA.  Enough CTAs for the FTL chains plus
@@ -414,7 +417,7 @@ int launch_scene_steps(rvh_ctx* ctx, int n, float dt, float& t) {      // t adva
     }
     const int e = scene_kernel_dispatch(ctx, wind, n, blocks, splat_bx, splat_bx * chunks, rpc);
     if (e != 0) { cudaGetLastError(); return fail(ctx, RVH_ERR_CUDA, std::string("cudaLaunchCooperativeKernel(k_scene_step): ") + cudaGetErrorString((cudaError_t)e)); }
-    ctx->scene_bar_base += 3u * (unsigned)n * (unsigned)blocks;         // the counter is monotonic (compared modulo 2^32)
+    ctx->scene_bar_base += (3u * (unsigned)n - 1u) * (unsigned)blocks;  // the counter is monotonic (compared modulo 2^32); no barrier after the last gather
     if (ctx->scene_timing) {                                            // tuning aid: mean duration of every phase and barrier over the launch's steps
         std::vector<unsigned long long> ts(1 + 6 * (size_t)n);
         CU(cudaStreamSynchronize(ctx->stream));

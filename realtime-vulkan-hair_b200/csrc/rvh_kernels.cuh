@@ -1220,7 +1220,7 @@ k_scene_step(const __grid_constant__ StepParams P, float* planes, float* corr, u
             q[3 * plane] = vx; q[4 * plane] = vy; q[5 * plane] = vz;
         }
         stamp();
-        scene_barrier(bar_counter, bar_target += gridDim.x);
+        if (step + 1 < nsteps) scene_barrier(bar_counter, bar_target += gridDim.x);   // the end of the launch is the last step's barrier
         stamp();
     }
 }
