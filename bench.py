@@ -464,12 +464,18 @@ def measure(R, rvh, args, workload, steps, warmup, scaling, full):
     if full and args.flags is not None:
         flags_s = args.flags
     S_total = S * R.world if scaling == "weak" else S
+    ids = None
     if scaling == "strong":
         lo, hi = rvh.scenes.shard_range(S_total, R.rank, R.world)
         first_strand, S = lo, hi - lo
     else:
         first_strand = R.rank * S
     device_init = args.device_init or S * N >= (1 << 26) or not full
+    if scaling == "strong" and R.world > 1 and workload != "c1" and os.environ.get("RVH_BENCH_STRONG_SHARDS", "spatial") == "spatial":
+        # ONE head over several GPUs: spatial domain decomposition (the ids sorted by the Morton code of their roots, cut into world
+        # pieces).  Contiguous id ranges would give every rank a uniformly thinned copy of the whole head (the generator hashes the id).
+        ids = rvh.scenes.spatial_shard_ids(S_total, R.rank, R.world, colliders=rvh.scenes.bench_colliders())
+        device_init = False
     flags = parse_flags(rvh, flags_s)
     grid_on = bool(flags & rvh.GRID_ON)
     rest = float(np.float32(L) / np.float32(N - 1))
@@ -483,14 +489,14 @@ def measure(R, rvh, args, workload, steps, warmup, scaling, full):
 
     aos_bytes = S * 48 * N
     pinned = host = None
-    if full or c1:
+    if full or c1 or ids is not None:
         # synthetic inputs in pinned host memory (global strand ids => every rank makes its own shard)
         pinned = torch.empty(aos_bytes // 4, dtype=torch.float32, pin_memory=True)
         host = pinned.numpy().reshape(S, 3, N, 4)
         if c1:
             host[:] = c1_state[first_strand:first_strand + S]
         elif not device_init:
-            rvh.scenes.synthetic_head(S, N, L, first_strand=first_strand, colliders=cols, out=host)
+            rvh.scenes.synthetic_head(S, N, L, first_strand=first_strand, colliders=cols, out=host, ids=ids)
 
     cfg = rvh.default_config(S, N, flags=flags, device=R.local, rest_length=rest, strands_per_thread=args.spt)
     sim = rvh.HairSim(cfg, rank=R.rank, nranks=R.world, nccl_id=R.new_nccl_id())
@@ -605,7 +611,7 @@ def measure(R, rvh, args, workload, steps, warmup, scaling, full):
     out = {"workload": workload, "value": value, "ms_per_step": ms / steps, "steps": steps, "roofline": roofline, "gpu_launches": int(launches),
            "clocks": clocks, "S": S, "S_total": S_total, "N": N, "flags_s": flags_s, "cols_nbytes": int(cols.nbytes),
            "implementation": {"scene_init": "reference scene frozen from Hair::Hair (tests/golden/c1_reference_scene.npz) + upload" if c1 else ("GPU (rvh_init_synthetic_head)" if device_init else "host (scenes.synthetic_head) + upload"),
-                              "parallelism": "strand-sharded x%d, grid exchange per step: %s" % (R.world, exchange) if R.world > 1 else "1 GPU", "numa": R.numa,
+                              "parallelism": "strand-sharded x%d%s, grid exchange per step: %s" % (R.world, " (spatial shards: ids in Morton order of their roots)" if ids is not None else "", exchange) if R.world > 1 else "1 GPU", "numa": R.numa,
                               "strands_per_thread": int(sim.cfg.strands_per_thread),
                               "step_n_fast_path": fast or "none",
                               "head_sdf": ("%s lattice, cell %.3f, sampled through %s" % ("x".join(str(d) for d in sdf_lattice()[0]), SDF_CELL, sdf_mode)) if flags & rvh.SDF_ON else None}}
@@ -693,7 +699,7 @@ def main():
             configs.append({"workload": w, "scaling": sc, "strands_total": c["S_total"], "points_per_strand": c["N"], "features": c["flags_s"],
                             "value": c["value"], "unit": UNIT, "ms_per_step": c["ms_per_step"], "steps": k, "dominant_kernel": r["kernel"].split(" ")[0], "roofline_frac": r["frac"], "ftl_frac": r["north_star_frac"],
                             "step_frac": r["step_frac"], "per_kernel_ms": r["per_kernel_ms"], "gpu_launches": c["gpu_launches"],
-                            "step_n_fast_path": c["implementation"]["step_n_fast_path"]})
+                            "step_n_fast_path": c["implementation"]["step_n_fast_path"], "parallelism": c["implementation"]["parallelism"]})
     checksum = None if args.no_checksum else verification_checksum(R, rvh)
 
     cpu = None

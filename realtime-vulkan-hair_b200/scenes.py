@@ -41,14 +41,58 @@ def _splitmix64(x):
     return z ^ (z >> np.uint64(31))
 
 
-def synthetic_head(num_strands, num_points, strand_length=2.5, first_strand=0, colliders=None, seed=8,
-                   chunk=1 << 18, out=None):
-    """Strand[S] AoS (float32 [S][3][N][4]) for global strand ids first_strand .. first_strand+S-1."""
+def _head_frames(colliders):
+    head = np.asarray(colliders, np.float32).reshape(-1, 48)[1]
+    return head[0:16].reshape(4, 4).T.astype(np.float32), head[32:48].reshape(4, 4).T.astype(np.float32)   # column-major -> [row][col]
+
+
+def _head_roots(sid, X, seed):
+    """Unit direction and root of the strands with global ids `sid` (uint64): the id is hashed, so consecutive ids are scattered."""
+    base = (np.uint64(seed) << np.uint64(32)) + np.uint64(2) * sid
+    r0 = (_splitmix64(base) >> np.uint64(40)).astype(np.float32) / np.float32(1 << 24)
+    r1 = (_splitmix64(base + np.uint64(1)) >> np.uint64(40)).astype(np.float32) / np.float32(1 << 24)
+    uy = r0
+    rad = np.sqrt(np.maximum(np.float32(1.0) - uy * uy, np.float32(0.0))).astype(np.float32)
+    phi = (np.float32(2.0 * np.pi) * r1).astype(np.float32)
+    u = np.stack([rad * np.cos(phi), uy, rad * np.sin(phi)], axis=1).astype(np.float32)
+    return u, (u @ X[:3, :3].T + X[:3, 3]).astype(np.float32)
+
+
+def spatial_shard_ids(num_strands_total, rank, nranks, colliders=None, seed=8, chunk=1 << 20):
+    """Strong scaling of ONE head over `nranks` GPUs as a spatial domain decomposition: the global strand ids sorted by the Morton
+    code of their roots (10 bits per axis over the reference's grid box), cut into `nranks` contiguous pieces; returns the ids of
+    piece `rank` (uint64, ascending Morton order).  Contiguous id ranges would hand every rank a uniformly thinned copy of the
+    whole head (the ids are hashed): fewer strands per voxel on every rank, which is what the splat's warp aggregation and the
+    collider candidate mask live on."""
     if colliders is None:
         colliders = reference_colliders()
-    head = np.asarray(colliders, np.float32).reshape(-1, 48)[1]
-    X = head[0:16].reshape(4, 4).T.astype(np.float32)          # column-major -> [row][col]
-    IT = head[32:48].reshape(4, 4).T.astype(np.float32)
+    X, _ = _head_frames(colliders)
+    S = int(num_strands_total)
+    keys = np.empty(S, np.uint64)
+    old = np.seterr(over="ignore")
+    try:
+        for lo in range(0, S, chunk):
+            hi = min(S, lo + chunk)
+            _, root = _head_roots(np.arange(lo, hi, dtype=np.uint64), X, seed)
+            q = np.clip(((root - np.array([-3.0, -2.0, -5.0], np.float32)) * np.float32(1024.0 / 7.0)).astype(np.int64), 0, 1023).astype(np.uint64)
+            k = np.zeros(hi - lo, np.uint64)
+            for b in range(10):
+                for a in range(3):
+                    k |= ((q[:, a] >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b + a)
+            keys[lo:hi] = k
+    finally:
+        np.seterr(**old)
+    order = np.argsort(keys, kind="stable").astype(np.uint64)
+    lo, hi = shard_range(S, rank, nranks)
+    return order[lo:hi]
+
+
+def synthetic_head(num_strands, num_points, strand_length=2.5, first_strand=0, colliders=None, seed=8,
+                   chunk=1 << 18, out=None, ids=None):
+    """Strand[S] AoS (float32 [S][3][N][4]) for global strand ids first_strand .. first_strand+S-1, or for the ids in `ids`."""
+    if colliders is None:
+        colliders = reference_colliders()
+    X, IT = _head_frames(colliders)
     S, N = int(num_strands), int(num_points)
     rest = np.float32(np.float32(strand_length) / np.float32(N - 1))
     if out is None:
@@ -58,15 +102,8 @@ def synthetic_head(num_strands, num_points, strand_length=2.5, first_strand=0, c
     try:
         for lo in range(0, S, chunk):
             hi = min(S, lo + chunk)
-            sid = (np.arange(lo, hi, dtype=np.uint64) + np.uint64(first_strand))
-            base = (np.uint64(seed) << np.uint64(32)) + np.uint64(2) * sid
-            r0 = (_splitmix64(base) >> np.uint64(40)).astype(np.float32) / np.float32(1 << 24)
-            r1 = (_splitmix64(base + np.uint64(1)) >> np.uint64(40)).astype(np.float32) / np.float32(1 << 24)
-            uy = r0
-            rad = np.sqrt(np.maximum(np.float32(1.0) - uy * uy, np.float32(0.0))).astype(np.float32)
-            phi = (np.float32(2.0 * np.pi) * r1).astype(np.float32)
-            u = np.stack([rad * np.cos(phi), uy, rad * np.sin(phi)], axis=1).astype(np.float32)
-            root = (u @ X[:3, :3].T + X[:3, 3]).astype(np.float32)
+            sid = (np.arange(lo, hi, dtype=np.uint64) + np.uint64(first_strand)) if ids is None else np.asarray(ids[lo:hi], np.uint64)
+            u, root = _head_roots(sid, X, seed)
             n = (u @ IT[:3, :3].T).astype(np.float32)
             n /= np.linalg.norm(n, axis=1, keepdims=True).astype(np.float32)
             d = n + np.float32(0.1) * np.array([0.05, 5.0, -2.0], np.float32)
