@@ -66,3 +66,26 @@ def test_reference_arm_processes_share_one_grid_bit_exactly():
         st, _, _ = orc.ref_dispatch(tag, st, cols, bench.DT, bench.DT * k)
     assert np.array_equal(got.view(np.uint32), st.view(np.uint32))
     assert np.abs(got[:, 1]).max() > 0
+
+
+def test_spatial_shards_partition_the_head_and_keep_every_strand():
+    """bench.py --scaling strong: the ids in Morton order of their roots, cut into `world` pieces.  The pieces are a partition of
+    the ids, each is spatially compact (a fraction of the head's bounding box), and a strand generated through `ids=` is the strand
+    the contiguous generator makes for that id."""
+    import numpy as np
+    import rvh_b200 as rvh
+    S, R = 20000, 8
+    pieces = [rvh.scenes.spatial_shard_ids(S, r, R) for r in range(R)]
+    allids = np.sort(np.concatenate(pieces))
+    assert np.array_equal(allids, np.arange(S, dtype=np.uint64))
+    assert max(len(p) for p in pieces) - min(len(p) for p in pieces) <= 1
+    whole = rvh.scenes.synthetic_head(S, 4, 2.5)
+    box = np.prod(whole[:, 0, 0, :3].max(0) - whole[:, 0, 0, :3].min(0))
+    fracs = []
+    for p in pieces:
+        part = rvh.scenes.synthetic_head(len(p), 4, 2.5, ids=p)
+        assert np.array_equal(part, whole[p.astype(np.int64)])
+        r = part[:, 0, 0, :3]
+        fracs.append(float(np.prod(r.max(0) - r.min(0)) / box))
+    # a contiguous id range covers the whole box (fraction ~1); a Morton range can straddle an octant boundary, so not every piece is small
+    assert np.median(fracs) < 0.4 and max(fracs) < 0.8, fracs
