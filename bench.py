@@ -671,7 +671,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE.json configurations appended as `configs`")
     ap.add_argument("--no-checksum", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: every rank owns the workload's strand count; strong: the count is split over the ranks")
     ap.add_argument("--no-kernel-events", action="store_true", help="time the steps without the per-kernel CUDA events (no roofline per-kernel split)")
     ap.add_argument("--expand", action="store_true", help="also time the guide -> render strand expansion (hair.tesc/hair.tese, 12 isolines x 42 divisions) of the final state")
