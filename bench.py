@@ -93,7 +93,7 @@ class ClockSampler:
         self.stop_flag = threading.Event()
         self.thread = None
         self.max_mhz = None
-        self.period = 0.025
+        self.period = float(os.environ.get("RVH_BENCH_SAMPLER_PERIOD", "0.025"))
 
     def _sample(self):
         import pynvml as nv

@@ -231,7 +231,7 @@ int rvh_debug_hit_masks(rvh_ctx* ctx, unsigned char* out, size_t bytes);
  * brackets its kernels with events; rvh_profile_read returns accumulated milliseconds
  * and launch counts since the last call: [0] ftl_step, [1] grid_gather, [2] grid
  * all-reduce, [3] grid clear, [4] grid_splat, [5] grid_finalize. */
-int rvh_profile_enable(rvh_ctx* ctx, int on);   /* 0 off, 1 every kernel, 2 only ftl_step (events between kernels cost ~3 us each) */
+int rvh_profile_enable(rvh_ctx* ctx, int on);   /* 0 off, 1 every kernel, 2 only ftl_step and only in every 4th step (events between kernels cost ~3 us each) */
 int rvh_profile_read(rvh_ctx* ctx, float ms[6], int launches[6]);
 
 int rvh_sync(rvh_ctx* ctx);
