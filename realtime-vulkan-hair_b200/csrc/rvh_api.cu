@@ -384,13 +384,17 @@ int scene_kernel_dispatch(rvh_ctx* ctx, bool wind, int n, int blocks, int splat_
 #undef RVH_SCENE
 }
 
-int launch_scene_steps(rvh_ctx* ctx, int n, float dt, float& t) {      // t advances exactly as n calls of rvh_step would move it
+// Returns kSceneFallback (and switches the path off for this context) when the device refuses the cooperative launch: the caller
+// then takes the launch-per-kernel step; nothing has been stepped and `t_io` is untouched in that case.
+constexpr int kSceneFallback = 1;
+int launch_scene_steps(rvh_ctx* ctx, int n, float dt, float& t_io) {   // t_io advances exactly as n calls of rvh_step would move it
     { int r = flush_gather(ctx); if (r) return r; }                     // an ordinary step left its gather to its successor: apply it now
     StepParams& P = ctx->P;
     const int flags = ctx->cfg.flags;
     const bool wind = flags & (RVH_WIND_A | RVH_WIND_B);
     P.dt = dt; P.inv_dt = 1.0f / dt; P.dt2 = dt * dt; P.vel_scale = P.damping / dt;
     P.wind_mode = (flags & RVH_WIND_B) ? 2 : ((flags & RVH_WIND_A) ? 1 : 0);
+    float t = t_io;
     for (int k = 0; k < n; ++k, t += dt) {
         float s2T = 0.f, T3 = 0.f, amp = 0.f;
         if (wind) wind_scalars(P.wind_mode, t, s2T, T3, amp);
@@ -400,7 +404,7 @@ int launch_scene_steps(rvh_ctx* ctx, int n, float dt, float& t) {      // t adva
     int& occ = ctx->scene_occupancy[wind ? 1 : 0][P.n_ell == 5 ? 1 : 0];  // co-resident CTAs per SM of this kernel variant: asked once (the per-frame call counts its host microseconds)
     if (occ == 0) occ = scene_kernel_dispatch(ctx, wind, n, 0, 0, 0, 0);
     const int per_sm = std::min(ctx->scene_ctas_per_sm, occ);
-    if (per_sm < 1) return fail(ctx, RVH_ERR_CUDA, "k_scene_step does not fit on an SM");
+    if (per_sm < 1) { ctx->scene_ctas_per_sm = 0; return kSceneFallback; }
     const int max_blocks = per_sm * ctx->num_sms;
     // The launch is sized to the scene, not to the machine: every barrier costs one atomic per CTA.  Enough CTAs for the FTL chains plus
     // a clearing crew beside them, for one splat item (128 strands x a chunk of rows) per CTA, and for one gather point per thread.
@@ -419,7 +423,7 @@ int launch_scene_steps(rvh_ctx* ctx, int n, float dt, float& t) {      // t adva
         ctx->scene_bar_base = 0u;
     }
     const int e = scene_kernel_dispatch(ctx, wind, n, blocks, splat_bx, splat_bx * chunks, rpc);
-    if (e != 0) { cudaGetLastError(); return fail(ctx, RVH_ERR_CUDA, std::string("cudaLaunchCooperativeKernel(k_scene_step): ") + cudaGetErrorString((cudaError_t)e)); }
+    if (e != 0) { cudaGetLastError(); ctx->scene_ctas_per_sm = 0; return kSceneFallback; }   // e.g. no cooperative launch under this driver configuration
     ctx->scene_bar_base += (3u * (unsigned)n - 1u) * (unsigned)blocks;  // the counter is monotonic (compared modulo 2^32); no barrier after the last gather
     if (ctx->scene_timing) {                                            // tuning aid: mean duration of every phase and barrier over the launch's steps
         std::vector<unsigned long long> ts(1 + 6 * (size_t)n);
@@ -432,6 +436,7 @@ int launch_scene_steps(rvh_ctx* ctx, int n, float dt, float& t) {      // t adva
     }
     ctx->launches += 1;
     ctx->gather_pending = false;                                        // applied inside the launch; the float grid was not produced
+    t_io = t;
     return RVH_OK;
 }
 
@@ -1161,7 +1166,8 @@ int rvh_step(rvh_ctx* ctx, float dt, float total_time) {
     CU(cudaSetDevice(ctx->cfg.device));
     if (dt > 0.f && scene_step_eligible(ctx) && !std::getenv("RVH_NO_FAST_STEP_N")) {   // small scene in its steady state: one launch per step
         float t = total_time;
-        return launch_scene_steps(ctx, 1, dt, t);
+        const int r = launch_scene_steps(ctx, 1, dt, t);
+        if (r != kSceneFallback) return r;
     }
     return do_step(ctx, dt, total_time, 3, true);
 }
@@ -1202,6 +1208,7 @@ int rvh_step_n(rvh_ctx* ctx, int n, float dt, float total_time0, float* ms_out) 
         while (done < n && scene_step_eligible(ctx)) {
             const int m = std::min(32, n - done);
             int r = launch_scene_steps(ctx, m, dt, t);
+            if (r == kSceneFallback) break;                             // the plain loop below takes the remaining steps
             if (r) return r;
             done += m;
         }
